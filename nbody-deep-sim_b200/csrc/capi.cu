@@ -1,0 +1,683 @@
+// C ABI of the engine (declared in include/nbody_b200.h): argument checks, launch planning, kernel launches.
+// Nothing here computes on the CPU; every entry point either launches sm_100a kernels or fails with a status.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nbody_b200.h"
+#include "batched.cuh"
+#include "energy.cuh"
+#include "force.cuh"
+#include "probe.cuh"
+
+namespace {
+
+using namespace nb;
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return status;
+}
+
+#define NB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(NBODY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define NB_LAUNCH_CHECK()                                                                                  \
+    do {                                                                                                   \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                                \
+        cudaError_t e_ = cudaGetLastError();                                                               \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(NBODY_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                         \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ device info
+
+struct DeviceInfo {
+    bool known = false;
+    int sms = 0;
+    int cc_major = 0;
+};
+constexpr int kMaxDevices = 64;
+DeviceInfo g_dev[kMaxDevices];
+std::mutex g_dev_mutex;
+
+int current_device_info(const DeviceInfo** out) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(NBODY_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    if (dev < 0 || dev >= kMaxDevices) return fail(NBODY_ERR_NO_DEVICE, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceInfo& d = g_dev[dev];
+    if (!d.known) {
+        NB_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        NB_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        d.known = true;
+    }
+    if (d.cc_major != 10)
+        return fail(NBODY_ERR_NO_DEVICE, "device %d has compute capability %d.x; this library is built for sm_100a only",
+                    dev, d.cc_major);
+    *out = &d;
+    return NBODY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ launch plan
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Kernel shapes. LARGE: 256 threads x 4 i-bodies, 2 CTAs/SM, 1024-body j tiles. SMALL: 128 threads x 2 i-bodies,
+// 4 CTAs/SM, 512-body j tiles (more, smaller CTAs so that mid-size N still fills 148 SMs).
+struct Shape {
+    int pairs, warps, min_blocks, tile_j;
+    int tile_i() const { return warps * 32 * pairs * 2; }
+};
+constexpr Shape kLarge{2, 8, 2, 1024};
+constexpr Shape kSmall{1, 4, 4, 512};
+constexpr int kMaxSplits = 16;
+constexpr int kPlanSms = 148;  // B200. Plans (and so workspace sizes) are a pure function of the problem size.
+
+struct Plan {
+    bool large;
+    int i_tiles;
+    int splits;  // per part
+    Shape shape() const { return large ? kLarge : kSmall; }
+};
+
+Plan plan_force(int n_local, int j_len) {
+    const int sms = kPlanSms;
+    Plan pl;
+    pl.large = n_local >= kLarge.tile_i() * sms;
+    const Shape sh = pl.shape();
+    pl.i_tiles = (n_local + sh.tile_i() - 1) / sh.tile_i();
+    const int slots = sms * sh.min_blocks;
+    int max_splits = j_len / (2 * sh.tile_j);
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > kMaxSplits) max_splits = kMaxSplits;
+    int best = 1;
+    double best_waste = 1e30;
+    for (int s = 1; s <= max_splits; ++s) {
+        const double ctas = double(pl.i_tiles) * s;
+        const double waves = ctas / slots;
+        const double waste = double((long long)((ctas + slots - 1) / slots)) / waves;
+        if (waste < best_waste - 1e-9) {
+            best_waste = waste;
+            best = s;
+        }
+        if (waste <= 1.03) break;  // good enough: prefer few splits
+    }
+    pl.splits = best;
+    return pl;
+}
+
+struct Workspace {
+    float4* bodies[2];
+    float* vhalf;
+    float4* partial;
+    unsigned* counters;
+    double* energy_partial;
+    double* energy_out;  // 2 doubles, scratch target when the caller wants no energies
+    int partial_stride;
+    size_t total;
+};
+constexpr size_t kCounterBytes = 64 * 1024;        // up to 16384 i-tiles
+constexpr size_t kEnergyPartialBytes = 512 * 1024;  // up to 65536 CTAs
+
+// Carves the workspace; with base == nullptr only sizes it. `own_bodies` = the body arrays live in the workspace.
+Workspace carve(void* base, int n_local, int n_total, int n_parts, bool own_bodies) {
+    Workspace w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    if (own_bodies) {
+        w.bodies[0] = static_cast<float4*>(take(size_t(n_total) * sizeof(float4)));
+        w.bodies[1] = static_cast<float4*>(take(size_t(n_total) * sizeof(float4)));
+        w.vhalf = static_cast<float*>(take(size_t(n_local) * 3 * sizeof(float)));
+    }
+    w.partial_stride = int(align_up(size_t(n_local), 32));
+    const int j_len = n_total / n_parts > 0 ? n_total / n_parts : 1;
+    const int slots = plan_force(n_local, j_len).splits * n_parts;
+    w.partial = static_cast<float4*>(take(size_t(slots) * w.partial_stride * sizeof(float4)));
+    w.counters = static_cast<unsigned*>(take(kCounterBytes));
+    w.energy_partial = static_cast<double*>(take(kEnergyPartialBytes));
+    w.energy_out = static_cast<double*>(take(256));
+    w.total = off;
+    return w;
+}
+
+size_t workspace_bytes_impl(int n_local, int n_total, int n_parts, bool own_bodies) {
+    return carve(nullptr, n_local, n_total, n_parts, own_bodies).total;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel launch
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    NB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+    return NBODY_OK;
+}
+
+template <int kPairs, int kWarps, int kMinBlocks, int kTileJ>
+int launch_force_shape(const ForceParams& p, int i_tiles, int splits, bool exact_diag, cudaStream_t stream) {
+    const size_t smem = TileRing<kTileJ, kStages, kWarps>::smem_bytes();
+    const dim3 grid(i_tiles, splits), block(kWarps * 32);
+    if (exact_diag) {
+        auto k = force_kernel<kPairs, kWarps, kMinBlocks, kTileJ, true>;
+        if (int st = set_smem(k, smem)) return st;
+        k<<<grid, block, smem, stream>>>(p);
+    } else {
+        auto k = force_kernel<kPairs, kWarps, kMinBlocks, kTileJ, false>;
+        if (int st = set_smem(k, smem)) return st;
+        k<<<grid, block, smem, stream>>>(p);
+    }
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+int launch_force(const Plan& pl, const ForceParams& p, cudaStream_t stream) {
+    // softening^2 below the smallest normal float is flushed by MUFU.RSQ: take the index-masked variant.
+    const bool exact_diag = !(p.eps2 >= 1.17549435e-38f);
+    if (pl.large)
+        return launch_force_shape<kLarge.pairs, kLarge.warps, kLarge.min_blocks, kLarge.tile_j>(p, pl.i_tiles, pl.splits,
+                                                                                              exact_diag, stream);
+    return launch_force_shape<kSmall.pairs, kSmall.warps, kSmall.min_blocks, kSmall.tile_j>(p, pl.i_tiles, pl.splits,
+                                                                                          exact_diag, stream);
+}
+
+int launch_prep(const PrepParams& p, cudaStream_t stream) {
+    prep_kernel<<<(p.n + 255) / 256, 256, 0, stream>>>(p);
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+int launch_energy(const float4* bodies, const float* vel, int n_total, int i_begin, int i_count, float g, float eps,
+                  double* cta_partial, double* out_uk, int sms, cudaStream_t stream) {
+    // Always the SMALL-like shape: 128 threads x 2 bodies; j split so that the grid covers the SMs a few times.
+    constexpr int kPairs = 1, kWarps = 4, kMinB = 4, kTileJ = 512;
+    constexpr int kTileI = kWarps * 32 * kPairs * 2;
+    const int i_tiles = (i_count + kTileI - 1) / kTileI;
+    int splits = (sms * kMinB * 2 + i_tiles - 1) / i_tiles;
+    const int max_splits = n_total / (2 * kTileJ) > 0 ? n_total / (2 * kTileJ) : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 64) splits = 64;
+    if (size_t(i_tiles) * splits * sizeof(double) > kEnergyPartialBytes)
+        splits = int(kEnergyPartialBytes / sizeof(double) / i_tiles);
+    if (splits < 1) return fail(NBODY_ERR_UNSUPPORTED, "energy: too many i-tiles (%d)", i_tiles);
+    EnergyParams ep{bodies, n_total, i_begin, i_count, eps, cta_partial};
+    auto k = potential_kernel<kPairs, kWarps, kMinB, kTileJ>;
+    const size_t smem = TileRing<kTileJ, kEnergyStages, kWarps>::smem_bytes();
+    if (int st = set_smem(k, smem)) return st;
+    k<<<dim3(i_tiles, splits), kWarps * 32, smem, stream>>>(ep);
+    NB_LAUNCH_CHECK();
+    EnergyFinishParams fp{cta_partial, i_tiles * splits, bodies, vel, i_begin, i_count, g, out_uk};
+    energy_finish_kernel<<<1, 1024, 0, stream>>>(fp);
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+int mode_of(int integrator, int* mode) {
+    if (integrator == NBODY_INTEGRATOR_LEAPFROG) {
+        *mode = MODE_LEAPFROG;
+        return NBODY_OK;
+    }
+    if (integrator == NBODY_INTEGRATOR_EULER) {
+        *mode = MODE_EULER;
+        return NBODY_OK;
+    }
+    return fail(NBODY_ERR_INVALID_ARGUMENT, "unknown integrator %d", integrator);
+}
+
+}  // namespace
+
+// ================================================================================================ exported API
+
+extern "C" {
+
+int nbody_version(void) { return 100; }
+
+const char* nbody_status_string(int status) {
+    switch (status) {
+        case NBODY_OK: return "ok";
+        case NBODY_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case NBODY_ERR_WORKSPACE: return "workspace too small";
+        case NBODY_ERR_CUDA: return "CUDA error";
+        case NBODY_ERR_NO_DEVICE: return "no usable sm_100 device";
+        case NBODY_ERR_UNSUPPORTED: return "unsupported shape";
+        default: return "unknown status";
+    }
+}
+
+const char* nbody_last_error(void) { return g_last_error.c_str(); }
+
+uint64_t nbody_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t nbody_workspace_bytes(int n_local, int n_total) {
+    if (n_local < 1 || n_total < n_local) return 0;
+    return workspace_bytes_impl(n_local, n_total, 1, true);
+}
+
+size_t nbody_shard_workspace_bytes(int n_local, int n_total, int n_parts) {
+    if (n_local < 1 || n_total < n_local || n_parts < 1) return 0;
+    return workspace_bytes_impl(n_local, n_total, n_parts, false);
+}
+
+int nbody_accel_f32(const float* pos, const float* mass, float* acc, int n, float g, float eps2, void* workspace,
+                    size_t workspace_bytes, void* stream_) {
+    if (!pos || !mass || !acc || !workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "accel: null pointer");
+    if (n < 1) return fail(NBODY_ERR_INVALID_ARGUMENT, "accel: n = %d", n);
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    Workspace w = carve(workspace, n, n, 1, true);
+    if (w.total > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "accel: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const Plan pl = plan_force(n, n);
+
+    PrepParams pp{};
+    pp.n = n, pp.i_begin = 0, pp.mode = MODE_ACCEL, pp.mass = mass, pp.pos = const_cast<float*>(pos);
+    pp.bodies = w.bodies[0];
+    if (int st = launch_prep(pp, stream)) return st;
+    if (pl.splits > 1) NB_CUDA(cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream));
+
+    ForceParams fp{};
+    fp.bodies = w.bodies[0], fp.j_begin = 0, fp.j_end = n, fp.i_begin = 0, fp.i_count = n;
+    fp.eps2 = eps2, fp.g = g;
+    fp.partial = w.partial, fp.partial_stride = w.partial_stride, fp.split_offset = 0, fp.splits_total = pl.splits;
+    fp.counters = w.counters;
+    fp.mode = MODE_ACCEL, fp.acc = acc;
+    return launch_force(pl, fp, stream);
+}
+
+int nbody_integrate_f32(int integrator, float* pos, float* vel, float* acc, const float* mass, int n, float g,
+                        float eps2, float eps, float dt, float half_dt, int steps, int record_every, float* traj,
+                        double* energies, float* step_ms, void* workspace, size_t workspace_bytes, void* stream_) {
+    int mode = MODE_ACCEL;
+    if (int st = mode_of(integrator, &mode)) return st;
+    if (!pos || !vel || !acc || !mass || !workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate: null pointer");
+    if (n < 1 || steps < 0) return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate: n = %d, steps = %d", n, steps);
+    if ((traj || energies) && record_every < 1)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate: record_every = %d", record_every);
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    Workspace w = carve(workspace, n, n, 1, true);
+    if (w.total > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "integrate: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    if (steps == 0) return NBODY_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const Plan pl = plan_force(n, n);
+
+    const size_t plane = size_t(n) * 3;
+    auto recorded = [&](int s) { return (traj || energies) && (s + 1) % record_every == 0; };
+    auto slot_of = [&](int s) { return size_t((s + 1) / record_every - 1); };
+    auto traj_plane = [&](int s, int which) -> float* {
+        return (traj && recorded(s)) ? traj + (slot_of(s) * 3 + which) * plane : nullptr;
+    };
+
+    std::vector<cudaEvent_t> events;
+    if (step_ms) {
+        events.resize(size_t(steps) + 1);
+        for (auto& e : events) NB_CUDA(cudaEventCreate(&e));
+    }
+    auto cleanup = [&]() {
+        for (auto& e : events) cudaEventDestroy(e);
+    };
+
+    int st = NBODY_OK;
+    do {
+        PrepParams pp{};
+        pp.n = n, pp.i_begin = 0, pp.mode = mode, pp.dt = dt, pp.half_dt = half_dt;
+        pp.mass = mass, pp.pos = pos, pp.vel = vel, pp.acc = acc, pp.vhalf = w.vhalf, pp.bodies = w.bodies[0];
+        pp.rec_pos = (mode == MODE_LEAPFROG) ? traj_plane(0, 0) : nullptr;
+        if ((st = launch_prep(pp, stream))) break;
+        if (pl.splits > 1) {
+            cudaError_t e = cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream);
+            if (e != cudaSuccess) {
+                st = fail(NBODY_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+                break;
+            }
+        }
+        if (step_ms) cudaEventRecord(events[0], stream);
+
+        for (int s = 0; s < steps && st == NBODY_OK; ++s) {
+            const int cur = s & 1;
+            ForceParams fp{};
+            fp.bodies = w.bodies[cur], fp.bodies_next = w.bodies[cur ^ 1];
+            fp.j_begin = 0, fp.j_end = n, fp.i_begin = 0, fp.i_count = n;
+            fp.eps2 = eps2, fp.g = g;
+            fp.partial = w.partial, fp.partial_stride = w.partial_stride, fp.split_offset = 0;
+            fp.splits_total = pl.splits, fp.counters = w.counters;
+            fp.mode = mode, fp.dt = dt, fp.half_dt = half_dt;
+            fp.pos = pos, fp.vel = vel, fp.acc = acc, fp.vhalf = w.vhalf;
+            fp.rec_vel = traj_plane(s, 1), fp.rec_acc = traj_plane(s, 2);
+            if (mode == MODE_LEAPFROG) {
+                fp.do_next = (s + 1 < steps);
+                fp.rec_pos = fp.do_next ? traj_plane(s + 1, 0) : nullptr;  // x of state s+1 is produced here
+            } else {
+                fp.do_next = 1;
+                fp.rec_pos = traj_plane(s, 0);
+            }
+            if ((st = launch_force(pl, fp, stream))) break;
+            if (energies && recorded(s)) {
+                // positions of state s: the buffer this launch consumed (leapfrog) or produced (euler)
+                const float4* state_bodies = (mode == MODE_LEAPFROG) ? w.bodies[cur] : w.bodies[cur ^ 1];
+                if ((st = launch_energy(state_bodies, vel, n, 0, n, g, eps, w.energy_partial,
+                                        energies + 2 * slot_of(s), dev->sms, stream)))
+                    break;
+            }
+            if (step_ms) cudaEventRecord(events[size_t(s) + 1], stream);
+        }
+    } while (0);
+
+    if (st == NBODY_OK && step_ms) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            st = fail(NBODY_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+        } else {
+            for (int s = 0; s < steps; ++s) cudaEventElapsedTime(&step_ms[s], events[s], events[size_t(s) + 1]);
+        }
+    }
+    cleanup();
+    return st;
+}
+
+int nbody_energies_f32(const float* pos, const float* vel, const float* mass, int n, float g, float eps,
+                       double* out_uk, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!pos || !vel || !mass || !out_uk || !workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "energies: null pointer");
+    if (n < 1) return fail(NBODY_ERR_INVALID_ARGUMENT, "energies: n = %d", n);
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    Workspace w = carve(workspace, n, n, 1, true);
+    if (w.total > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "energies: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PrepParams pp{};
+    pp.n = n, pp.i_begin = 0, pp.mode = MODE_ACCEL, pp.mass = mass, pp.pos = const_cast<float*>(pos);
+    pp.bodies = w.bodies[0];
+    if (int st = launch_prep(pp, stream)) return st;
+    return launch_energy(w.bodies[0], vel, n, 0, n, g, eps, w.energy_partial, out_uk, dev->sms, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ sharded path
+
+int nbody_shard_prepare_f32(int integrator, float* pos, const float* vel, const float* acc, const float* mass,
+                            float* vhalf, float* bodies, int i_begin, int n_local, float dt, float half_dt,
+                            void* stream_) {
+    int mode = MODE_ACCEL;
+    if (integrator != 0)
+        if (int st = mode_of(integrator, &mode)) return st;
+    if (!pos || !mass || !bodies) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_prepare: null pointer");
+    if (mode == MODE_LEAPFROG && (!vel || !acc || !vhalf))
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_prepare: leapfrog needs vel, acc, vhalf");
+    if (n_local < 1 || i_begin < 0) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_prepare: bad range");
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    PrepParams pp{};
+    pp.n = n_local, pp.i_begin = i_begin, pp.mode = mode, pp.dt = dt, pp.half_dt = half_dt;
+    pp.mass = mass, pp.pos = pos, pp.vel = vel, pp.acc = acc, pp.vhalf = vhalf;
+    pp.bodies = reinterpret_cast<float4*>(bodies);
+    return launch_prep(pp, static_cast<cudaStream_t>(stream_));
+}
+
+int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_next, int n_total, int i_begin,
+                          int n_local, int j_begin, int j_end, int part, int n_parts, float* pos, float* vel,
+                          float* acc, float* vhalf, float g, float eps2, float dt, float half_dt, int do_next,
+                          void* workspace, size_t workspace_bytes, void* stream_) {
+    int mode = MODE_ACCEL;
+    if (integrator != 0)
+        if (int st = mode_of(integrator, &mode)) return st;
+    if (!bodies || !acc || !workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_force: null pointer");
+    if (mode != MODE_ACCEL && (!pos || !vel || !bodies_next))
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_force: integrator needs pos, vel, bodies_next");
+    if (mode == MODE_LEAPFROG && !vhalf) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_force: leapfrog needs vhalf");
+    if (n_local < 1 || i_begin < 0 || i_begin + n_local > n_total || j_begin < 0 || j_end > n_total ||
+        j_begin >= j_end || part < 0 || part >= n_parts)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_force: bad range (i %d+%d, j [%d,%d), part %d/%d, n %d)", i_begin,
+                    n_local, j_begin, j_end, part, n_parts, n_total);
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    Workspace w = carve(workspace, n_local, n_total, n_parts, false);
+    if (w.total > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "shard_force: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    // Every part uses the split count planned for an even share of the j range, so slots are known up front.
+    const Plan pl = plan_force(n_local, n_total / n_parts > 0 ? n_total / n_parts : 1);
+    if (part == 0 && n_parts * pl.splits > 1)
+        NB_CUDA(cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream));
+    ForceParams fp{};
+    fp.bodies = reinterpret_cast<const float4*>(bodies), fp.bodies_next = reinterpret_cast<float4*>(bodies_next);
+    fp.j_begin = j_begin, fp.j_end = j_end, fp.i_begin = i_begin, fp.i_count = n_local;
+    fp.eps2 = eps2, fp.g = g;
+    fp.partial = w.partial, fp.partial_stride = w.partial_stride;
+    fp.split_offset = part * pl.splits, fp.splits_total = n_parts * pl.splits, fp.counters = w.counters;
+    fp.mode = mode, fp.do_next = do_next, fp.dt = dt, fp.half_dt = half_dt;
+    fp.pos = pos, fp.vel = vel, fp.acc = acc, fp.vhalf = vhalf;
+    return launch_force(pl, fp, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ batched path
+
+int nbody_batched_max_n(void) { return kBatchedThreads * 2 * 4; }
+
+static int batched_launch(int mode, float* pos, float* vel, float* acc, const float* mass, int n_systems, int n,
+                          float g, float eps2, float dt, float half_dt, int steps, int record_every, float* traj,
+                          cudaStream_t stream) {
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    BatchedParams p{};
+    p.n = n, p.mode = mode, p.steps = steps, p.record_every = record_every > 0 ? record_every : 1;
+    p.g = g, p.eps2 = eps2, p.dt = dt, p.half_dt = half_dt;
+    p.mass = mass, p.pos = pos, p.vel = vel, p.acc = acc, p.traj = traj, p.n_systems = n_systems;
+    const size_t smem = size_t(2) * n * sizeof(float4);
+    const bool exact = !(eps2 >= 1.17549435e-38f);
+    const int pairs = (n + 2 * kBatchedThreads - 1) / (2 * kBatchedThreads);
+#define NB_BATCHED(P, E)                                              \
+    do {                                                              \
+        auto k = batched_kernel<P, E>;                                \
+        if (int st = set_smem(k, smem)) return st;                    \
+        k<<<n_systems, kBatchedThreads, smem, stream>>>(p);           \
+    } while (0)
+    if (pairs <= 1) {
+        if (exact) NB_BATCHED(1, true); else NB_BATCHED(1, false);
+    } else if (pairs == 2) {
+        if (exact) NB_BATCHED(2, true); else NB_BATCHED(2, false);
+    } else {
+        if (exact) NB_BATCHED(4, true); else NB_BATCHED(4, false);
+    }
+#undef NB_BATCHED
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+int nbody_batched_integrate_f32(int integrator, float* pos, float* vel, float* acc, const float* mass,
+                                int n_systems, int n, float g, float eps2, float dt, float half_dt, int steps,
+                                int record_every, float* traj, void* stream_) {
+    int mode = MODE_ACCEL;
+    if (int st = mode_of(integrator, &mode)) return st;
+    if (!pos || !vel || !acc || !mass) return fail(NBODY_ERR_INVALID_ARGUMENT, "batched_integrate: null pointer");
+    if (n_systems < 1 || n < 1 || steps < 0)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "batched_integrate: n_systems = %d, n = %d, steps = %d", n_systems, n,
+                    steps);
+    if (n > nbody_batched_max_n())
+        return fail(NBODY_ERR_UNSUPPORTED, "batched_integrate: n = %d exceeds %d", n, nbody_batched_max_n());
+    if (traj && record_every < 1) return fail(NBODY_ERR_INVALID_ARGUMENT, "batched_integrate: record_every = %d", record_every);
+    if (steps == 0) return NBODY_OK;
+    return batched_launch(mode, pos, vel, acc, mass, n_systems, n, g, eps2, dt, half_dt, steps, record_every, traj,
+                          static_cast<cudaStream_t>(stream_));
+}
+
+int nbody_batched_accel_f32(const float* pos, const float* mass, float* acc, int n_systems, int n, float g,
+                            float eps2, void* stream_) {
+    if (!pos || !acc || !mass) return fail(NBODY_ERR_INVALID_ARGUMENT, "batched_accel: null pointer");
+    if (n_systems < 1 || n < 1) return fail(NBODY_ERR_INVALID_ARGUMENT, "batched_accel: n_systems = %d, n = %d", n_systems, n);
+    if (n > nbody_batched_max_n())
+        return fail(NBODY_ERR_UNSUPPORTED, "batched_accel: n = %d exceeds %d", n, nbody_batched_max_n());
+    // MODE_ACCEL only reads pos; vel is never dereferenced for writing, pass pos to keep the loads in bounds.
+    return batched_launch(MODE_ACCEL, const_cast<float*>(pos), const_cast<float*>(pos), acc, mass, n_systems, n, g, eps2,
+                          0.f, 0.f, 0, 1, nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+// ------------------------------------------------------------------------------------------------ host path
+
+namespace {
+struct HostCache {
+    cudaStream_t stream = nullptr;
+    void* buf = nullptr;
+    size_t bytes = 0;
+};
+HostCache g_host[kMaxDevices];
+std::mutex g_host_mutex;
+
+int host_scratch(int device, size_t bytes, HostCache** out) {
+    if (device < 0 || device >= kMaxDevices) return fail(NBODY_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", device);
+    NB_CUDA(cudaSetDevice(device));
+    HostCache& c = g_host[device];
+    if (!c.stream) NB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (c.bytes < bytes) {
+        if (c.buf) NB_CUDA(cudaFree(c.buf));
+        c.buf = nullptr, c.bytes = 0;
+        NB_CUDA(cudaMalloc(&c.buf, bytes));
+        c.bytes = bytes;
+    }
+    *out = &c;
+    return NBODY_OK;
+}
+}  // namespace
+
+int nbody_accel_host_f32(const float* pos, const float* mass, float* acc, int n, float g, float eps2, int device,
+                         uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (!pos || !mass || !acc) return fail(NBODY_ERR_INVALID_ARGUMENT, "accel_host: null pointer");
+    if (n < 1) return fail(NBODY_ERR_INVALID_ARGUMENT, "accel_host: n = %d", n);
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    const size_t b3 = align_up(size_t(n) * 12, 256), b1 = align_up(size_t(n) * 4, 256);
+    const size_t ws = nbody_workspace_bytes(n, n);
+    HostCache* c;
+    if (int st = host_scratch(device, 2 * b3 + b1 + ws, &c)) return st;
+    char* base = static_cast<char*>(c->buf);
+    float* d_pos = reinterpret_cast<float*>(base);
+    float* d_acc = reinterpret_cast<float*>(base + b3);
+    float* d_mass = reinterpret_cast<float*>(base + 2 * b3);
+    void* d_ws = base + 2 * b3 + b1;
+    NB_CUDA(cudaMemcpyAsync(d_pos, pos, size_t(n) * 12, cudaMemcpyHostToDevice, c->stream));
+    NB_CUDA(cudaMemcpyAsync(d_mass, mass, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+    if (int st = nbody_accel_f32(d_pos, d_mass, d_acc, n, g, eps2, d_ws, ws, c->stream)) return st;
+    NB_CUDA(cudaMemcpyAsync(acc, d_acc, size_t(n) * 12, cudaMemcpyDeviceToHost, c->stream));
+    NB_CUDA(cudaStreamSynchronize(c->stream));
+    if (h2d_bytes) *h2d_bytes = uint64_t(n) * 16;
+    if (d2h_bytes) *d2h_bytes = uint64_t(n) * 12;
+    return NBODY_OK;
+}
+
+int nbody_integrate_host_f32(int integrator, float* pos, float* vel, float* acc, const float* mass, int n, float g,
+                             float eps2, float eps, float dt, float half_dt, int steps, int record_every,
+                             float* traj, double* energies, float* step_ms, int device, uint64_t* h2d_bytes,
+                             uint64_t* d2h_bytes) {
+    if (!pos || !vel || !acc || !mass) return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate_host: null pointer");
+    if (n < 1 || steps < 0) return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate_host: n = %d, steps = %d", n, steps);
+    if ((traj || energies) && record_every < 1)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate_host: record_every = %d", record_every);
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    const size_t slots = (traj || energies) ? size_t(steps / record_every) : 0;
+    const size_t b3 = align_up(size_t(n) * 12, 256), b1 = align_up(size_t(n) * 4, 256);
+    const size_t b_traj = traj ? align_up(slots * 3 * size_t(n) * 12, 256) : 0;
+    const size_t b_en = energies ? align_up(slots * 2 * sizeof(double), 256) : 0;
+    const size_t ws = nbody_workspace_bytes(n, n);
+    HostCache* c;
+    if (int st = host_scratch(device, 3 * b3 + b1 + b_traj + b_en + ws, &c)) return st;
+    char* base = static_cast<char*>(c->buf);
+    float* d_pos = reinterpret_cast<float*>(base);
+    float* d_vel = reinterpret_cast<float*>(base + b3);
+    float* d_acc = reinterpret_cast<float*>(base + 2 * b3);
+    float* d_mass = reinterpret_cast<float*>(base + 3 * b3);
+    float* d_traj = traj ? reinterpret_cast<float*>(base + 3 * b3 + b1) : nullptr;
+    double* d_en = energies ? reinterpret_cast<double*>(base + 3 * b3 + b1 + b_traj) : nullptr;
+    void* d_ws = base + 3 * b3 + b1 + b_traj + b_en;
+    NB_CUDA(cudaMemcpyAsync(d_pos, pos, size_t(n) * 12, cudaMemcpyHostToDevice, c->stream));
+    NB_CUDA(cudaMemcpyAsync(d_vel, vel, size_t(n) * 12, cudaMemcpyHostToDevice, c->stream));
+    NB_CUDA(cudaMemcpyAsync(d_acc, acc, size_t(n) * 12, cudaMemcpyHostToDevice, c->stream));
+    NB_CUDA(cudaMemcpyAsync(d_mass, mass, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+    if (int st = nbody_integrate_f32(integrator, d_pos, d_vel, d_acc, d_mass, n, g, eps2, eps, dt, half_dt, steps,
+                                     record_every, d_traj, d_en, step_ms, d_ws, ws, c->stream))
+        return st;
+    NB_CUDA(cudaMemcpyAsync(pos, d_pos, size_t(n) * 12, cudaMemcpyDeviceToHost, c->stream));
+    NB_CUDA(cudaMemcpyAsync(vel, d_vel, size_t(n) * 12, cudaMemcpyDeviceToHost, c->stream));
+    NB_CUDA(cudaMemcpyAsync(acc, d_acc, size_t(n) * 12, cudaMemcpyDeviceToHost, c->stream));
+    if (traj && slots) NB_CUDA(cudaMemcpyAsync(traj, d_traj, slots * 3 * size_t(n) * 12, cudaMemcpyDeviceToHost, c->stream));
+    if (energies && slots)
+        NB_CUDA(cudaMemcpyAsync(energies, d_en, slots * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NB_CUDA(cudaStreamSynchronize(c->stream));
+    if (h2d_bytes) *h2d_bytes = uint64_t(n) * 40;
+    if (d2h_bytes)
+        *d2h_bytes = uint64_t(n) * 36 + (traj ? slots * 3 * uint64_t(n) * 12 : 0) + (energies ? slots * 16 : 0);
+    return NBODY_OK;
+}
+
+int nbody_host_cache_release(void) {
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    for (int d = 0; d < kMaxDevices; ++d) {
+        HostCache& c = g_host[d];
+        if (!c.buf && !c.stream) continue;
+        NB_CUDA(cudaSetDevice(d));
+        if (c.buf) NB_CUDA(cudaFree(c.buf));
+        if (c.stream) NB_CUDA(cudaStreamDestroy(c.stream));
+        c = HostCache{};
+    }
+    return NBODY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ measurement
+
+int nbody_probe_fp32_peak(int device, int packed, double* tflops) {
+    if (!tflops) return fail(NBODY_ERR_INVALID_ARGUMENT, "probe: null pointer");
+    NB_CUDA(cudaSetDevice(device));
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    float* d_out;
+    NB_CUDA(cudaMalloc(&d_out, 256));
+    cudaEvent_t e0, e1;
+    NB_CUDA(cudaEventCreate(&e0));
+    NB_CUDA(cudaEventCreate(&e1));
+    const int blocks = dev->sms * 8, outer = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {  // first reps warm the clocks; keep the best
+        NB_CUDA(cudaEventRecord(e0, 0));
+        if (packed)
+            fma_probe_kernel<true><<<blocks, 256>>>(d_out, outer, 1.0000001f, 1e-9f);
+        else
+            fma_probe_kernel<false><<<blocks, 256>>>(d_out, outer, 1.0000001f, 1e-9f);
+        NB_LAUNCH_CHECK();
+        NB_CUDA(cudaEventRecord(e1, 0));
+        NB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        NB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = double(blocks) * 256 * double(outer) * kProbeInner * kProbeChains * 2 /*lanes*/ * 2 /*fma*/;
+        const double tf = flops / (double(ms) * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+    return NBODY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// Total potential and kinetic energy, as the reference defines them.
+//
+// Replaces (reference, read-only): src/galaxify/simulation.py:91-115 (BaseSimulator.compute_energies):
+//   k = sum_i 0.5 * m_i * |v_i|^2
+//   u = sum_{i<j} -G m_i m_j / (|r_i - r_j| + eps)        <- softening enters as |r| + eps, NOT sqrt(r^2+eps^2)
+//
+// The pair sum is evaluated as -G/2 * sum_i m_i * phi_i with phi_i = sum_{j != i} m_j / (|r_ij| + eps), on the
+// same TMA-fed j-tile ring as the force kernel. Per interaction: 3 FADD2 + 3 FMUL2/FFMA2 (r^2) + MUFU.SQRT +
+// FADD2 + MUFU.RCP + FFMA2, so this kernel is MUFU-bound (2 MUFU per interaction), and it is kept apart from the
+// force kernel for that reason. The self term is masked by index (the reference masks the diagonal with +inf,
+// simulation.py:107-108); distinct coincident bodies contribute m_i m_j / eps exactly as there.
+// Tile sums are FP32, everything across tiles / threads / CTAs is FP64, and every cross-CTA sum is taken in a
+// fixed order, so the result is deterministic and closer to the exact value than the reference's FP32 reduction.
+#pragma once
+#include "async_copy.cuh"
+
+namespace nb {
+
+constexpr int kEnergyStages = 4;
+constexpr int kEnergyLookahead = 2;
+
+struct EnergyParams {
+    const float4* bodies;  // (x,y,z,m), all n_total bodies
+    int n_total;
+    int i_begin, i_count;
+    float eps;
+    double* cta_partial;  // [gridDim.y][gridDim.x] : sum over the CTA's i-bodies of m_i * phi_i (its j split)
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int kBlock>
+__device__ __forceinline__ double block_sum(double v, double* scratch /* kBlock/32 doubles */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double total = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kBlock / 32; ++w) total += scratch[w];
+    return total;  // valid on thread 0
+}
+
+template <int kPairs, int kWarps, int kMinBlocks, int kTileJ>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(const EnergyParams p) {
+    constexpr int kCT = kWarps * 32;
+    constexpr int kI = 2 * kPairs;
+    constexpr int kTileI = kCT * kI;
+    using Ring = TileRing<kTileJ, kEnergyStages, kWarps>;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_red[kWarps];
+
+    const int tid = threadIdx.x;
+    const int nj = p.n_total;
+    const int per = (nj + gridDim.y - 1) / gridDim.y;
+    const int j0 = min(int(blockIdx.y) * per, nj);
+    const int j1 = min(int(blockIdx.y + 1) * per, nj);
+
+    Ring ring;
+    ring.attach(smem_raw, p.bodies + j0, j1 - j0);
+    const int ntiles = ring.num_tiles();
+    if (tid == 0) ring.init_barriers();
+    __syncthreads();
+    if (tid == 0)
+        for (int t = 0; t < min(kEnergyLookahead, ntiles); ++t) ring.issue(t);
+
+    const int tile_base = blockIdx.x * kTileI;
+    float4 me[kI];
+    int gi[kI];
+    bool valid[kI];
+    float2 nx[kPairs], ny[kPairs], nz[kPairs];
+#pragma unroll
+    for (int k = 0; k < kI; ++k) {
+        const int li = tile_base + k * kCT + tid;
+        valid[k] = li < p.i_count;
+        gi[k] = p.i_begin + min(li, p.i_count - 1);
+        me[k] = p.bodies[gi[k]];
+    }
+#pragma unroll
+    for (int q = 0; q < kPairs; ++q) {
+        nx[q] = make_float2(-me[2 * q].x, -me[2 * q + 1].x);
+        ny[q] = make_float2(-me[2 * q].y, -me[2 * q + 1].y);
+        nz[q] = make_float2(-me[2 * q].z, -me[2 * q + 1].z);
+    }
+    double phi[kI];
+#pragma unroll
+    for (int k = 0; k < kI; ++k) phi[k] = 0.0;
+    const float2 eps = make_float2(p.eps, p.eps);
+
+    for (int t = 0; t < ntiles; ++t) {
+        if (tid == 0 && t + kEnergyLookahead < ntiles) ring.issue(t + kEnergyLookahead);
+        const int jt = j0 + t * kTileJ;
+        const int count = ring.tile_count(t);
+        const float4* __restrict__ tj = ring.tile(t);
+        float2 acc[kPairs];
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) acc[q] = make_float2(0.f, 0.f);
+        ring.wait(t);
+#pragma unroll 4
+        for (int jj = 0; jj < count; ++jj) {
+            const float4 b = tj[jj];
+            const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
+            const float2 bm = make_float2(b.w, b.w);
+            const int jg = jt + jj;
+#pragma unroll
+            for (int q = 0; q < kPairs; ++q) {
+                const float2 dx = __fadd2_rn(bx, nx[q]);
+                const float2 dy = __fadd2_rn(by, ny[q]);
+                const float2 dz = __fadd2_rn(bz, nz[q]);
+                float2 r2 = __fmul2_rn(dx, dx);
+                r2 = __ffma2_rn(dy, dy, r2);
+                r2 = __ffma2_rn(dz, dz, r2);
+                const float2 d = __fadd2_rn(make_float2(sqrt_approx(r2.x), sqrt_approx(r2.y)), eps);
+                float2 inv = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+                if (jg == gi[2 * q]) inv.x = 0.f;
+                if (jg == gi[2 * q + 1]) inv.y = 0.f;
+                acc[q] = __ffma2_rn(bm, inv, acc[q]);
+            }
+        }
+        ring.release(t);
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+            phi[2 * q] += double(acc[q].x);
+            phi[2 * q + 1] += double(acc[q].y);
+        }
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < kI; ++k)
+        if (valid[k]) mine += double(me[k].w) * phi[k];
+    const double total = block_sum<kCT>(mine, s_red);
+    if (tid == 0) p.cta_partial[size_t(blockIdx.y) * gridDim.x + blockIdx.x] = total;
+}
+
+// Single-CTA finish: u = -G/2 * sum(cta_partial) and k = sum 0.5 m v^2, both in fixed order.
+struct EnergyFinishParams {
+    const double* cta_partial;
+    int n_partials;
+    const float4* bodies;  // for the masses, global index
+    const float* vel;      // (i_count,3), local index
+    int i_begin, i_count;
+    float g;
+    double* out_uk;  // (u, k); with accumulate != 0 the values are added (sharded ranks sum afterwards)
+};
+
+__global__ void __launch_bounds__(1024) energy_finish_kernel(const EnergyFinishParams p) {
+    __shared__ double s_red[32];
+    double u = 0.0;
+    for (int i = threadIdx.x; i < p.n_partials; i += 1024) u += p.cta_partial[i];
+    const double u_tot = block_sum<1024>(u, s_red);
+    __syncthreads();
+    double k = 0.0;
+    for (int i = threadIdx.x; i < p.i_count; i += 1024) {
+        const float vx = p.vel[3 * i], vy = p.vel[3 * i + 1], vz = p.vel[3 * i + 2];
+        // per-body term in FP32 exactly as simulation.py:100: 0.5 * m * (vx^2 + vy^2 + vz^2)
+        const float v2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+        k += double(__fmul_rn(__fmul_rn(0.5f, p.bodies[p.i_begin + i].w), v2));
+    }
+    const double k_tot = block_sum<1024>(k, s_red);
+    if (threadIdx.x == 0) {
+        p.out_uk[0] = -0.5 * double(p.g) * u_tot;
+        p.out_uk[1] = k_tot;
+    }
+}
+
+}  // namespace nb

@@ -1,0 +1,64 @@
+"""Shared fixtures. GPU tests are marked `gpu` and call the CUDA path through the C ABI; everything else runs on CPU."""
+
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "nbody-deep-sim_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+class Golden:
+    """One tests/golden/*.npz: outputs of the unmodified reference (see tests/golden/make_golden.py)."""
+
+    def __init__(self, path):
+        self.name = os.path.splitext(os.path.basename(path))[0]
+        z = np.load(path)
+        self.z = z
+        self.meta = json.loads(str(z["meta"]))
+        self.sim = self.meta["sim"]
+        self.integrator = self.meta["integrator"]
+        self.n = self.meta["n"]
+        self.steps = int(z["steps"])
+        self.keep = [int(s) for s in z["keep"]]
+
+    def __getitem__(self, key):
+        return self.z[key]
+
+    def __repr__(self):
+        return self.name
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name) -> Golden:
+    return Golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+@pytest.fixture(params=golden_names())
+def golden(request) -> Golden:
+    return load_golden(request.param)
+
+
+def rel_rows(a, b):
+    """Per-particle relative error ||a_i - b_i|| / ||b_i||, rows with ||b_i|| = 0 compared absolutely."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    num = np.linalg.norm(a - b, axis=-1)
+    den = np.linalg.norm(b, axis=-1)
+    return np.where(den > 0, num / np.where(den > 0, den, 1.0), num)

@@ -1,0 +1,119 @@
+"""Parity of the CUDA path (through the C ABI) against the reference's golden vectors and the CPU oracle.
+
+Tolerances (north_star): per-step accelerations within 1e-5 relative (FP32) per particle; trajectories at the s01
+parameters within 1e-6 of max|x| and max|v| over 1,000 steps (SURVEY.md §8a derives why that horizon is
+rounding-dominated, not chaotic); energies within 1e-5 relative of the reference's own FP32 energies.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_rows
+
+pytestmark = pytest.mark.gpu
+
+ACC_RTOL = 1e-5
+TRAJ_RTOL = 1e-6
+ENERGY_RTOL = 1e-5
+
+
+def make_sim(g, calc_energy=False):
+    from galaxify import simulation
+
+    cls = simulation.LeapFrogSimulator if g.integrator == "leapfrog" else simulation.EulerSimulator
+    return cls(positions=g["ic_pos"], velocities=g["ic_vel"], masses=g["ic_mass"], calc_energy=calc_energy,
+               device="cuda", **g.sim)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_initial_accelerations_match_reference(name):
+    g = load_golden(name)
+    sim = make_sim(g)
+    acc = sim.accelerations.cpu().numpy()
+    assert acc.shape == (g.n, 3) and acc.dtype == np.float32
+    assert np.all(np.isfinite(acc))
+    assert rel_rows(acc, g["acc0"]).max() <= ACC_RTOL
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_trajectory_matches_reference(name):
+    g = load_golden(name)
+    sim = make_sim(g)
+    states = sim.run(g.steps)
+    assert [s.step for s in states] == list(range(g.steps))
+    chaotic = g.sim["g_const"] == 1.0  # BaseSimulator defaults: real dynamics, short horizon -> looser bound
+    tol = 1e-4 if chaotic else TRAJ_RTOL
+    for k, s in enumerate(g.keep):
+        st = states[s]
+        assert st.positions.device.type == "cpu" and st.positions.shape == (g.n, 3)
+        for got, want in ((st.positions, g["pos"][k]), (st.velocities, g["vel"][k])):
+            scale = max(np.abs(want).max(), 1e-30)
+            assert np.abs(got.numpy() - want).max() <= tol * scale, (name, s)
+        assert rel_rows(st.accelerations.numpy(), g["acc"][k]).max() <= (1e-3 if chaotic else ACC_RTOL), (name, s)
+    # the simulator's own state is the last recorded state
+    np.testing.assert_array_equal(sim.positions.cpu().numpy(), states[-1].positions.numpy())
+    np.testing.assert_array_equal(sim.velocities.cpu().numpy(), states[-1].velocities.numpy())
+    np.testing.assert_array_equal(sim.accelerations.cpu().numpy(), states[-1].accelerations.numpy())
+
+
+@pytest.mark.parametrize("name", ["disk_n1024_leapfrog", "spiral_n500_euler", "disk_n3_leapfrog", "spiral_n25_leapfrog"])
+def test_energies_match_reference(name):
+    g = load_golden(name)
+    sim = make_sim(g, calc_energy=True)
+    u0, k0 = sim.compute_energies()
+    assert abs(u0 - float(g["u0"])) <= ENERGY_RTOL * abs(float(g["u0"]))
+    assert abs(k0 - float(g["k0"])) <= ENERGY_RTOL * abs(float(g["k0"]))
+    states = sim.run(g.steps)
+    u = np.array([s.u_energy for s in states])
+    k = np.array([s.k_energy for s in states])
+    assert np.abs(u - g["u"]).max() <= ENERGY_RTOL * np.abs(g["u"]).max()
+    assert np.abs(k - g["k"]).max() <= ENERGY_RTOL * np.abs(g["k"]).max()
+    # energy drift no worse than the reference's (its own energy definition), with 10% slack for FP32 noise
+    e, e_ref = u + k, g["u"] + g["k"]
+    drift = abs(e[-1] - e[0]) / abs(e[0])
+    drift_ref = abs(e_ref[-1] - e_ref[0]) / abs(e_ref[0])
+    assert drift <= 1.1 * drift_ref + 1e-6
+
+
+def test_step_by_step_equals_run():
+    """step() x k and run(k) walk the same rounding sequence (the fused epilogue re-opens the step like prep does)."""
+    g = load_golden("spiral_n500_leapfrog")
+    a, b = make_sim(g), make_sim(g)
+    for _ in range(7):
+        a.step()
+    states = b.run(7)
+    np.testing.assert_array_equal(a.positions.cpu().numpy(), states[-1].positions.numpy())
+    np.testing.assert_array_equal(a.velocities.cpu().numpy(), states[-1].velocities.numpy())
+    np.testing.assert_array_equal(a.accelerations.cpu().numpy(), states[-1].accelerations.numpy())
+
+
+@pytest.mark.parametrize("n", [2, 31, 257, 1000, 4096, 5000, 16384, 40000])
+def test_accelerations_vs_oracle_ragged_sizes(n):
+    """Sizes around the tile boundaries (128/256/512/1024) and the split-j plans, disk ICs, vs the FP64 oracle."""
+    from galaxify import galaxies, simulation
+    from oracle import c_oracle
+
+    pos, vel, mass = galaxies.generate_disk(n_bodies=n, total_mass=1.0, radial_scale=3.0, height_scale=0.3,
+                                            g_const=4.5e-6, black_hole_mass=0.01, seed=n)
+    sim = simulation.LeapFrogSimulator(positions=pos, velocities=vel, masses=mass, g_const=4.5e-6, softening=0.05,
+                                       dt=1e-4, calc_energy=False)
+    acc = sim.accelerations.cpu().numpy()
+    hi = min(n, 2048)
+    want = c_oracle.accelerations_f64(pos, mass, 4.5e-6, 0.05, 0, hi)
+    err = rel_rows(acc[:hi], want)
+    assert err.max() <= ACC_RTOL, err.max()
+    want_tail = c_oracle.accelerations_f64(pos, mass, 4.5e-6, 0.05, max(0, n - 300), n)
+    assert rel_rows(acc[max(0, n - 300):], want_tail).max() <= ACC_RTOL
+
+
+def test_momentum_drift_no_worse_than_reference():
+    g = load_golden("disk_n1024_leapfrog")
+    sim = make_sim(g)
+    m = g["ic_mass"].astype(np.float64)[:, None]
+    states = sim.run(g.steps)
+    p_first = (m * states[0].velocities.numpy().astype(np.float64)).sum(0)
+    p_last = (m * states[-1].velocities.numpy().astype(np.float64)).sum(0)
+    ref_first = (m * g["vel"][0].astype(np.float64)).sum(0)
+    ref_last = (m * g["vel"][-1].astype(np.float64)).sum(0)
+    assert np.linalg.norm(p_last - p_first) <= 1.5 * np.linalg.norm(ref_last - ref_first) + 1e-12
