@@ -1,0 +1,202 @@
+"""i-sharded large-N simulators: one process per GPU, positions all-gathered every step over NCCL.
+
+An addition with no reference counterpart (the reference is single-device, simulation.py:46-51). The constructor
+keeps the reference's keyword arguments; every rank passes the SAME full arrays and keeps only its slice.
+
+Layout: the body array (x,y,z,m float4) has world_size slots of `n_pad = ceil(n / world_size)` bodies; rank r owns
+global indices [r*n_pad, r*n_pad + count_r). Padding bodies are never read: each step is a set of j-range "parts",
+one per rank slice (adjacent slices merge when there is no padding), and parts only cover real bodies.
+
+One step on a rank (leapfrog; Euler differs only in the epilogue):
+    all_gather(bodies_cur)  [NCCL stream]   ||   force(part = own slice)  [compute stream]
+    wait for the gather, force(remaining parts); the last part to finish runs the fused kick/kick/drift epilogue
+    and writes the rank's slice of bodies_next, which the next step gathers.
+The force accumulates into the same split-j scratch as the single-GPU path, so a rank computes exactly what the
+single-GPU kernel computes for its i-bodies up to FP32 summation order (the j splits differ).
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native
+from .simulation import SimulationState, _ptr
+
+
+def shard_layout(n: int, world_size: int):
+    """(n_pad, counts): slot size and the number of real bodies in every rank's slot."""
+    n_pad = (n + world_size - 1) // world_size
+    counts = [max(0, min(n_pad, n - r * n_pad)) for r in range(world_size)]
+    return n_pad, counts
+
+
+def step_parts(rank: int, n_pad: int, counts):
+    """j ranges (global slot indices) of one step for `rank`: own slice first, then the other ranks' slices with
+    adjacent ones merged (slices are adjacent exactly when the earlier slot has no padding)."""
+    parts = [(rank * n_pad, rank * n_pad + counts[rank])]
+    for r, c in enumerate(counts):
+        if r == rank or c == 0:
+            continue
+        lo, hi = r * n_pad, r * n_pad + c
+        if len(parts) > 1 and parts[-1][1] == lo:
+            parts[-1] = (parts[-1][0], hi)
+        else:
+            parts.append((lo, hi))
+    return parts
+
+
+class ShardedSimulator:
+    _integrator = None
+
+    def __init__(self, *, positions, velocities, masses, g_const: float = 1.0, softening: float = 0.1,
+                 dt: float = 0.01, calc_energy: bool = False, device: str = None, group=None):
+        if device is not None and device not in ["cuda", "cpu"]:
+            raise ValueError("device debe ser 'cuda', 'cpu' o None")
+        if calc_energy:
+            raise NotImplementedError("sharded simulators do not compute energies yet")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+        self.dt, self.g_const, self.softening, self.calc_energy = dt, g_const, softening, calc_energy
+        self.device = self._pick_device(device)
+
+        pos = np.asarray(positions, dtype=np.float32)
+        vel = np.asarray(velocities, dtype=np.float32)
+        mass = np.asarray(masses, dtype=np.float32)
+        self.n = pos.shape[0]
+        if pos.shape != (self.n, 3) or vel.shape != (self.n, 3) or mass.shape != (self.n,):
+            raise ValueError("expected positions (n,3), velocities (n,3), masses (n,)")
+        self.n_pad, self.counts = shard_layout(self.n, self.world_size)
+        self.n_local = self.counts[self.rank]
+        if min(self.counts) < 1:
+            raise ValueError(f"n = {self.n} is too small to shard over {self.world_size} ranks")
+        self.i_begin = self.rank * self.n_pad
+        lo = self.rank * self.n_pad
+        sl = slice(lo, lo + self.n_local)
+        dev = self.device
+        self.positions = torch.tensor(pos[sl], device=dev)
+        self.velocities = torch.tensor(vel[sl], device=dev)
+        self.masses = torch.tensor(mass[sl], device=dev)
+        self.accelerations = torch.zeros_like(self.positions)
+        self._vhalf = torch.zeros_like(self.positions)
+        self._bodies = [torch.zeros((self.world_size * self.n_pad, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._parts = step_parts(self.rank, self.n_pad, self.counts)
+        self._workspace = self._alloc_workspace()
+        self.launches_per_step = len(self._parts)
+        # initial accelerations (simulation.py:69)
+        self._prepare(0, self._bodies[0])
+        self._gather(self._bodies[0]).wait()
+        self._force_all(0, self._bodies[0], None, do_next=0)
+
+    # ------------------------------------------------------------------ device plumbing (overridden by CPU tests)
+
+    def _pick_device(self, device):
+        if device == "cpu":
+            raise RuntimeError("galaxify (B200 engine) has no CPU path")
+        _native.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("galaxify (B200 engine) needs a CUDA device and found none; there is no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _alloc_workspace(self):
+        need = _native.lib().nbody_shard_workspace_bytes(self.n_local, self.world_size * self.n_pad, len(self._parts))
+        return torch.empty(need, dtype=torch.uint8, device=self.device)
+
+    def _scalars(self):
+        return dict(g=_native.f32(self.g_const), eps2=_native.f32(self.softening**2), dt=_native.f32(self.dt),
+                    half_dt=_native.f32(0.5 * self.dt))
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _prepare(self, integrator, bodies):
+        s = self._scalars()
+        _native.call("nbody_shard_prepare_f32", integrator, _ptr(self.positions), _ptr(self.velocities),
+                     _ptr(self.accelerations), _ptr(self.masses), _ptr(self._vhalf), _ptr(bodies), self.i_begin,
+                     self.n_local, s["dt"], s["half_dt"], self._stream())
+
+    def _force(self, integrator, bodies, bodies_next, part, j_range, do_next):
+        s = self._scalars()
+        ws = self._workspace
+        _native.call("nbody_shard_force_f32", integrator, _ptr(bodies), _ptr(bodies_next),
+                     self.world_size * self.n_pad, self.i_begin, self.n_local, j_range[0], j_range[1], part,
+                     len(self._parts), _ptr(self.positions), _ptr(self.velocities), _ptr(self.accelerations),
+                     _ptr(self._vhalf), s["g"], s["eps2"], s["dt"], s["half_dt"], do_next, _ptr(ws), ws.numel(),
+                     self._stream())
+
+    def _gather(self, bodies):
+        """In-place all-gather of every rank's slot; returns the async work handle."""
+        mine = bodies[self.i_begin : self.i_begin + self.n_pad]
+        return dist.all_gather_into_tensor(bodies, mine, group=self.group, async_op=True)
+
+    # ------------------------------------------------------------------ stepping
+
+    def _force_all(self, integrator, bodies, bodies_next, do_next, gather_work=None):
+        """Own part first (overlaps the gather), then the remote parts; the last launch runs the epilogue."""
+        self._force(integrator, bodies, bodies_next, 0, self._parts[0], do_next)
+        if gather_work is not None:
+            gather_work.wait()
+        for part in range(1, len(self._parts)):
+            self._force(integrator, bodies, bodies_next, part, self._parts[part], do_next)
+
+    def _advance(self, steps: int, on_state=None):
+        if steps <= 0:
+            return
+        integ = self._integrator
+        cur = 0
+        self._prepare(integ, self._bodies[cur])
+        for s in range(steps):
+            work = self._gather(self._bodies[cur])
+            do_next = 1 if (integ == _native.INTEGRATOR_EULER or s + 1 < steps) else 0
+            self._force_all(integ, self._bodies[cur], self._bodies[cur ^ 1], do_next, work)
+            if on_state is not None:
+                # leapfrog: the drift of the NEXT step already went into self.positions; state s sits in the
+                # buffer this step consumed. Euler: state s is what the epilogue just wrote.
+                src = self._bodies[cur] if integ == _native.INTEGRATOR_LEAPFROG else self._bodies[cur ^ 1]
+                on_state(s, src[self.i_begin : self.i_begin + self.n_local, :3])
+            cur ^= 1
+
+    def step(self):
+        if self._integrator is None:
+            raise NotImplementedError("El método step debe ser implementado en la subclase")
+        self._advance(1)
+
+    def run(self, steps: int, record_every: int = 1) -> list[SimulationState]:
+        """Like BaseSimulator.run (simulation.py:117-146); the recorded tensors hold this rank's slice only."""
+        if self._integrator is None:
+            raise NotImplementedError("El método step debe ser implementado en la subclase")
+        states = []
+
+        def record(s, pos_view):
+            if (s + 1) % record_every == 0:
+                states.append(SimulationState(step=s, step_time=float("nan"), positions=pos_view.cpu(),
+                                              velocities=self.velocities.cpu(),
+                                              accelerations=self.accelerations.cpu()))
+
+        self._advance(steps, record)
+        return states
+
+    def gather_state(self):
+        """Full (positions, velocities, accelerations) on every rank, as CPU tensors in the original body order."""
+        out = []
+        for t in (self.positions, self.velocities, self.accelerations):
+            padded = torch.zeros((self.n_pad, 3), dtype=t.dtype, device=t.device)
+            padded[: self.n_local] = t
+            full = torch.empty((self.world_size * self.n_pad, 3), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(full, padded, group=self.group)
+            rows = [full[r * self.n_pad : r * self.n_pad + c] for r, c in enumerate(self.counts)]
+            out.append(torch.cat(rows).cpu())
+        return tuple(out)
+
+
+class ShardedLeapFrogSimulator(ShardedSimulator):
+    _integrator = _native.INTEGRATOR_LEAPFROG
+
+
+class ShardedEulerSimulator(ShardedSimulator):
+    _integrator = _native.INTEGRATOR_EULER

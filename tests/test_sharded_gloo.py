@@ -1,0 +1,158 @@
+"""world_size-2 (and 3) CPU tests of the i-sharded host logic over gloo.
+
+The product path's device calls (`_prepare`, `_force`: C-ABI kernels) are replaced, in this test only, by an
+emulation built on the CPU oracle, so that what is exercised is the part that has no GPU in it: the slot layout,
+the j-range parts, the in-place all-gather, the step protocol (own part first, epilogue on the last part, the
+leapfrog re-opening) and the state recording. The result must equal the single-process oracle run.
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT, load_golden
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _emulated_class(base):
+    """Subclass of a sharded simulator whose two device calls are oracle-backed CPU emulations."""
+    from oracle import galaxify_oracle as oracle
+
+    f = np.float32
+
+    class Emulated(base):
+        def _pick_device(self, device):
+            return torch.device("cpu")
+
+        def _alloc_workspace(self):
+            return {"sum": None, "seen": 0}
+
+        def _prepare(self, integrator, bodies):
+            pos, vel, acc = self.positions.numpy(), self.velocities.numpy(), self.accelerations.numpy()
+            if integrator == 1:  # opening half-kick + drift, separately rounded (simulation.py:164-166)
+                vh = vel + f(0.5 * self.dt) * acc
+                self._vhalf.copy_(torch.from_numpy(vh))
+                pos += f(self.dt) * vh
+            sl = slice(self.i_begin, self.i_begin + self.n_local)
+            bodies[sl, :3] = torch.from_numpy(pos)
+            bodies[sl, 3] = self.masses
+
+        def _force(self, integrator, bodies, bodies_next, part, j_range, do_next):
+            ws = self._workspace
+            if part == 0:
+                ws["sum"], ws["seen"] = np.zeros((self.n_local, 3)), 0
+            b = bodies.numpy()
+            lo, hi = j_range
+            mine = b[self.i_begin : self.i_begin + self.n_local]
+            # un-scaled partial sum of this j range for the local bodies, FP64 (the kernel: FP32 tiles + Kahan)
+            both = np.concatenate([mine, b[lo:hi]])
+            full = oracle.accelerations_f64(both[:, :3], both[:, 3], 1.0, self.softening, rows=slice(0, self.n_local))
+            own = oracle.accelerations_f64(mine[:, :3], mine[:, 3], 1.0, self.softening)
+            overlap = self.i_begin >= lo and self.i_begin < hi  # the part IS the own slice
+            ws["sum"] += own if overlap else full - own
+            ws["seen"] += 1
+            if ws["seen"] < len(self._parts):
+                return
+            a = (f(self.g_const) * ws["sum"].astype(f)).astype(f)
+            self.accelerations.copy_(torch.from_numpy(a))
+            if integrator == 0:
+                return
+            pos, vel = self.positions.numpy(), self.velocities.numpy()
+            if integrator == 1:
+                h = f(0.5 * self.dt)
+                v = self._vhalf.numpy() + h * a
+                vel[:] = v
+                if not do_next:
+                    return
+                v = v + h * a
+                self._vhalf.copy_(torch.from_numpy(v))
+            else:
+                v = vel + f(self.dt) * a
+                vel[:] = v
+            pos += f(self.dt) * v
+            sl = slice(self.i_begin, self.i_begin + self.n_local)
+            bodies_next[sl, :3] = torch.from_numpy(pos)
+            bodies_next[sl, 3] = self.masses
+
+    return Emulated
+
+
+def _worker(rank, world, port, case, integrator, steps, out_dir):
+    import sys
+
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from galaxify import sharded
+
+        g = load_golden(case)
+        base = sharded.ShardedLeapFrogSimulator if integrator == "leapfrog" else sharded.ShardedEulerSimulator
+        sim = _emulated_class(base)(positions=g["ic_pos"], velocities=g["ic_vel"], masses=g["ic_mass"], **g.sim)
+        acc0 = sim.gather_state()[2].numpy()
+        states = sim.run(steps)
+        pos, vel, acc = (t.numpy() for t in sim.gather_state())
+        first = states[0].positions.numpy()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), acc0=acc0, pos=pos, vel=vel, acc=acc, first=first,
+                 n_states=len(states), i_begin=sim.i_begin, n_local=sim.n_local)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,case,integrator", [(2, "spiral_n25_leapfrog", "leapfrog"),
+                                                   (2, "disk_n500_euler", "euler"),
+                                                   (3, "disk_n500_leapfrog", "leapfrog")])
+def test_sharded_protocol_matches_single_process_oracle(tmp_path, world, case, integrator):
+    from oracle import galaxify_oracle as oracle
+
+    steps = 5
+    mp.spawn(_worker, args=(world, _free_port(), case, integrator, steps, str(tmp_path)), nprocs=world, join=True)
+    g = load_golden(case)
+    ref, st = oracle.run(g["ic_pos"], g["ic_vel"], g["ic_mass"], integrator=integrator, steps=steps, **g.sim)
+    acc0 = oracle.accelerations(g["ic_pos"], g["ic_mass"], g.sim["g_const"], g.sim["softening"]).numpy()
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), f"r{r}.npz"))
+        assert int(z["n_states"]) == steps
+        scale = lambda a: max(np.abs(a).max(), 1e-30)
+        assert np.abs(z["acc0"] - acc0).max() <= 2e-6 * scale(acc0)
+        assert np.abs(z["pos"] - ref[steps - 1]["pos"]).max() <= 1e-6 * scale(ref[steps - 1]["pos"])
+        assert np.abs(z["vel"] - ref[steps - 1]["vel"]).max() <= 1e-6 * scale(ref[steps - 1]["vel"])
+        assert np.abs(z["acc"] - ref[steps - 1]["acc"]).max() <= 2e-6 * scale(ref[steps - 1]["acc"])
+        lo, cnt = int(z["i_begin"]), int(z["n_local"])
+        n_pad = -(-g.n // world)
+        first_rows = slice(r * n_pad, r * n_pad + cnt)
+        assert np.abs(z["first"] - ref[0]["pos"][first_rows]).max() <= 1e-6 * scale(ref[0]["pos"])
+
+
+def test_layout_and_parts_cover_every_body_exactly_once():
+    from galaxify.sharded import shard_layout, step_parts
+
+    for n, world in ((16, 4), (17, 4), (1 << 20, 8), (5, 2), (1000, 3), (262144, 8)):
+        n_pad, counts = shard_layout(n, world)
+        assert sum(counts) == n and max(counts) == n_pad
+        for rank in range(world):
+            parts = step_parts(rank, n_pad, counts)
+            assert parts[0] == (rank * n_pad, rank * n_pad + counts[rank])
+            covered = np.zeros(world * n_pad, dtype=int)
+            for lo, hi in parts:
+                covered[lo:hi] += 1
+            real = np.zeros(world * n_pad, dtype=int)
+            for r, c in enumerate(counts):
+                real[r * n_pad : r * n_pad + c] = 1
+            np.testing.assert_array_equal(covered, real)
+            if n % world == 0:
+                assert len(parts) <= 3
