@@ -39,6 +39,9 @@ UNIT = "interactions/s"
 FLOPS_PER_INTERACTION = 20.0  # BASELINE.json north_star
 S01 = dict(g_const=4.5e-6, softening=0.05, dt=1e-4)  # s01-dataset-generation.py:44-50 defaults
 L2_FLUSH_BYTES = 256 << 20
+# dram__bytes_read.sum + dram__bytes_write.sum of one force_kernel launch at N = 1,048,576, from the round-1
+# `ncu --set full` capture of this command (profiles/r1_ncu_force_kernel_n1m.txt): 31.27 MB + 14.69 MB.
+NCU_TRAFFIC_BYTES_N1M = 45_952_000
 
 
 def make_system(n):
@@ -335,7 +338,9 @@ def main():
             achieved = FLOPS_PER_INTERACTION * n * n / world / (k_ms * 1e-3) / 1e12
             kernel = f"force launches of one rank ({res['launches_per_step'] - 1} per step), per-GPU share of the step"
         line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peaks["ffma2"], "unit": "TFLOP/s",
-                            "frac": achieved / peaks["ffma2"], "traffic": None, "kernel": kernel,
+                            "frac": achieved / peaks["ffma2"],
+                            "traffic": NCU_TRAFFIC_BYTES_N1M if (world == 1 and n == 1 << 20) else None,
+                            "kernel": kernel,
                             "kernel_ms": k_ms,
                             "peak_source": "measured live: nbody_probe_fp32_peak (register-resident FFMA2 chains, "
                                            "best of 6); MEASURED_PEAKS.json has no FP32 entry",

@@ -110,7 +110,7 @@ __device__ __forceinline__ void epilogue_body(const ForceParams& p, int li, floa
 
 // kExactDiag: softening^2 underflows FP32 (or is 0), so the self term would be 0*inf. Mask it by index, which is
 // what fill_diagonal_(0) does in the reference (simulation.py:85); two distinct coincident bodies still give NaN there.
-template <int kPairs, int kWarps, int kMinBlocks, int kTileJ, bool kExactDiag>
+template <int kPairs, int kWarps, int kMinBlocks, int kTileJ, bool kExactDiag, int kUnroll = 4>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const ForceParams p) {
     constexpr int kCT = kWarps * 32;  // threads
     constexpr int kI = 2 * kPairs;    // i-bodies per thread
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const Fo
 
         ring.wait(t);
 
-#pragma unroll 4
+#pragma unroll kUnroll
         for (int jj = 0; jj < count; ++jj) {
             const float4 b = tj[jj];
             const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
