@@ -21,74 +21,79 @@ import numpy as np
 import torch
 
 
-def _f32(x) -> torch.Tensor:
-    return torch.as_tensor(np.asarray(x), dtype=torch.float32).contiguous()
+def _f32(x, device="cpu") -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32).contiguous()
+    return torch.as_tensor(np.asarray(x), dtype=torch.float32).contiguous().to(device)
 
 
-def accelerations(pos, mass, g_const: float, softening: float, rows: slice | None = None, chunk: int | None = None):
+def accelerations(pos, mass, g_const: float, softening: float, rows: slice | None = None, chunk: int | None = None,
+                  device="cpu"):
     """FP32 accelerations of the bodies in `rows` (default: all) — simulation.py:71-89.
 
     diff[i,j] = r_j - r_i (:80); dist_sq = sum(diff^2) + softening^2 (:82, the Python double is cast to FP32 by the
     add); inv = dist_sq^-1.5 (:83); diagonal forced to 0 (:85); acc = G * sum_j diff * inv * m_j (:86-88).
-    `chunk` bounds the number of i-rows materialised at once.
+    `chunk` bounds the number of i-rows materialised at once. `device="cuda"` runs the same operators on the GPU,
+    i.e. the reference's own `device="cuda"` path (simulation.py:46-51), used as the on-box oracle where the CPU is
+    too slow (tools/validate_config2.py).
     """
-    pos = _f32(pos)
-    mass = _f32(mass)
+    pos = _f32(pos, device)
+    mass = _f32(mass, device)
     n = pos.shape[0]
     lo, hi, _ = (rows or slice(None)).indices(n)
     if chunk is None:
         chunk = max(1, min(hi - lo, (256 << 20) // max(1, 12 * n)))  # ~256 MB per (rows,N,3) temporary
-    out = torch.empty((hi - lo, 3), dtype=torch.float32)
+    out = torch.empty((hi - lo, 3), dtype=torch.float32, device=pos.device)
     for a in range(lo, hi, chunk):
         b = min(hi, a + chunk)
         diff = pos.unsqueeze(0) - pos[a:b].unsqueeze(1)  # (rows, N, 3): r_j - r_i
         dist_sq = (diff**2).sum(dim=2) + softening**2
         inv_dist_cube = dist_sq.pow(-1.5)
-        idx = torch.arange(a, b)
+        idx = torch.arange(a, b, device=pos.device)
         inv_dist_cube[idx - a, idx] = 0  # the rows' share of fill_diagonal_(0)
         out[a - lo : b - lo] = g_const * (diff * inv_dist_cube.unsqueeze(2) * mass.unsqueeze(0).unsqueeze(2)).sum(dim=1)
     return out
 
 
-def energies(pos, vel, mass, g_const: float, softening: float, chunk: int | None = None):
+def energies(pos, vel, mass, g_const: float, softening: float, chunk: int | None = None, device="cpu"):
     """(u_energy, k_energy) — simulation.py:91-115. Softening enters as |r| + eps (:105).
 
     Unchunked (the default up to N = 8192) it is the reference's operator sequence; chunked, the upper-triangle sum
     is accumulated row block by row block in FP64.
     """
-    pos, vel, mass = _f32(pos), _f32(vel), _f32(mass)
+    pos, vel, mass = _f32(pos, device), _f32(vel, device), _f32(mass, device)
     n = pos.shape[0]
     kinetic = 0.5 * mass * (vel**2).sum(dim=1)
     k_energy = kinetic.sum().item()
     if chunk is None and n <= 8192:
         diff = pos.unsqueeze(0) - pos.unsqueeze(1)
         dist = (diff**2).sum(dim=2).sqrt() + softening
-        dist.masked_fill_(torch.eye(n, dtype=torch.bool), float("inf"))
+        dist.masked_fill_(torch.eye(n, dtype=torch.bool, device=pos.device), float("inf"))
         potential = -g_const * (mass.unsqueeze(0) * mass.unsqueeze(1)) / dist
         return potential.triu(1).sum().item(), k_energy
     chunk = chunk or max(1, (256 << 20) // max(1, 12 * n))
     u = 0.0
-    cols = torch.arange(n)
+    cols = torch.arange(n, device=pos.device)
     for a in range(0, n, chunk):
         b = min(n, a + chunk)
         diff = pos.unsqueeze(0) - pos[a:b].unsqueeze(1)
         dist = (diff**2).sum(dim=2).sqrt() + softening
         potential = -g_const * (mass.unsqueeze(0) * mass[a:b].unsqueeze(1)) / dist
-        upper = cols.unsqueeze(0) > torch.arange(a, b).unsqueeze(1)  # j > i
-        u += torch.where(upper, potential, torch.zeros(())).sum(dtype=torch.float64).item()
+        upper = cols.unsqueeze(0) > torch.arange(a, b, device=pos.device).unsqueeze(1)  # j > i
+        u += torch.where(upper, potential, torch.zeros((), device=pos.device)).sum(dtype=torch.float64).item()
     return u, k_energy
 
 
 class State:
     """Mutable (positions, velocities, accelerations, masses) in FP32, as BaseSimulator holds them (:58-69)."""
 
-    def __init__(self, pos, vel, mass, g_const=1.0, softening=0.1, dt=0.01):
-        self.pos, self.vel, self.mass = _f32(pos).clone(), _f32(vel).clone(), _f32(mass).clone()
-        self.g_const, self.softening, self.dt = g_const, softening, dt
-        self.acc = accelerations(self.pos, self.mass, g_const, softening)  # :69
+    def __init__(self, pos, vel, mass, g_const=1.0, softening=0.1, dt=0.01, device="cpu", chunk=None):
+        self.pos, self.vel, self.mass = _f32(pos, device).clone(), _f32(vel, device).clone(), _f32(mass, device).clone()
+        self.g_const, self.softening, self.dt, self.device, self.chunk = g_const, softening, dt, device, chunk
+        self.acc = self._force()  # :69
 
     def _force(self):
-        return accelerations(self.pos, self.mass, self.g_const, self.softening)
+        return accelerations(self.pos, self.mass, self.g_const, self.softening, chunk=self.chunk, device=self.device)
 
     def leapfrog_step(self):
         """Kick-drift-kick, simulation.py:164-170: each update is a rounded multiply followed by a rounded add."""
@@ -104,23 +109,24 @@ class State:
         self.pos += self.dt * self.vel
 
     def energies(self):
-        return energies(self.pos, self.vel, self.mass, self.g_const, self.softening)
+        return energies(self.pos, self.vel, self.mass, self.g_const, self.softening, device=self.device)
 
 
 def run(pos, vel, mass, *, integrator: str, steps: int, g_const=1.0, softening=0.1, dt=0.01, calc_energy=False,
-        keep=None):
+        keep=None, device="cpu", chunk=None):
     """The loop of BaseSimulator.run (simulation.py:117-146) over a State.
 
     Returns {step: dict(pos, vel, acc[, u, k])} for the 0-based steps in `keep` (default: all), plus the State.
     """
-    st = State(pos, vel, mass, g_const, softening, dt)
+    st = State(pos, vel, mass, g_const, softening, dt, device=device, chunk=chunk)
     advance = {"leapfrog": st.leapfrog_step, "euler": st.euler_step}[integrator]
     keep = set(range(steps)) if keep is None else set(keep)
     out = {}
     for s in range(steps):
         advance()
         if s in keep:
-            rec = dict(pos=st.pos.clone().numpy(), vel=st.vel.clone().numpy(), acc=st.acc.clone().numpy())
+            rec = dict(pos=st.pos.cpu().clone().numpy(), vel=st.vel.cpu().clone().numpy(),
+                       acc=st.acc.cpu().clone().numpy())
             if calc_energy:
                 rec["u"], rec["k"] = st.energies()
             out[s] = rec
@@ -142,7 +148,8 @@ def accelerations_f64(pos, mass, g_const: float, softening: float, rows: slice |
         b = min(hi, a + chunk)
         diff = p[None, :, :] - p[a:b, None, :]
         d2 = (diff * diff).sum(axis=2) + eps2
-        inv = d2**-1.5
+        with np.errstate(divide="ignore"):  # softening = 0 puts 0**-1.5 on the (masked) diagonal
+            inv = d2**-1.5
         inv[np.arange(b - a), np.arange(a, b)] = 0.0
         out[a - lo : b - lo] = g * np.einsum("ijk,ij,j->ik", diff, inv, m)
     return out

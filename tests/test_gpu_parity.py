@@ -117,3 +117,32 @@ def test_momentum_drift_no_worse_than_reference():
     ref_first = (m * g["vel"][0].astype(np.float64)).sum(0)
     ref_last = (m * g["vel"][-1].astype(np.float64)).sum(0)
     assert np.linalg.norm(p_last - p_first) <= 1.5 * np.linalg.norm(ref_last - ref_first) + 1e-12
+
+
+@pytest.mark.parametrize("config", ["merger_262144", "disk_1048576"])
+def test_large_n_sampled_rows_vs_fp64_oracle(config):
+    """BASELINE.json configs[3] and [4]: beyond the reference's reach (O(N^2) memory), so the kernel is checked on a
+    sample of i-bodies against the FP64 C oracle over ALL j-bodies."""
+    from galaxify import galaxies, simulation
+    from oracle import c_oracle
+
+    kw = dict(total_mass=1.0, radial_scale=3.0, height_scale=0.3, g_const=4.5e-6, black_hole_mass=0.01)
+    if config == "merger_262144":
+        a = galaxies.generate_disk(n_bodies=131072, seed=1, **kw)
+        b = galaxies.generate_disk(n_bodies=131072, seed=2, offset=(12.0, 3.0, 1.0), initial_vel=(-2e-4, 0.0, 0.0),
+                                   angle=(0.4, 0.0, 0.3), **kw)
+        pos, vel, mass = galaxies.merge(a, b)
+    else:
+        pos, vel, mass = galaxies.generate_disk(n_bodies=1 << 20, seed=5, **kw)
+    n = len(mass)
+    sim = simulation.LeapFrogSimulator(positions=pos, velocities=vel, masses=mass, g_const=4.5e-6, softening=0.05,
+                                       dt=1e-4, calc_energy=False)
+    sim.step()
+    acc = sim.accelerations.cpu().numpy()
+    x1 = sim.positions.cpu().numpy()
+    worst = 0.0
+    for lo in (0, 1000, n // 2 - 64, n // 2, n - 128):
+        want = c_oracle.accelerations_f64(x1, mass, 4.5e-6, 0.05, lo, lo + 128)
+        worst = max(worst, rel_rows(acc[lo : lo + 128], want).max())
+    assert worst <= ACC_RTOL, worst
+    assert np.isfinite(acc).all()
