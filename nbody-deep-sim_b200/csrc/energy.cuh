@@ -4,11 +4,12 @@
 //   k = sum_i 0.5 * m_i * |v_i|^2
 //   u = sum_{i<j} -G m_i m_j / (|r_i - r_j| + eps)        <- softening enters as |r| + eps, NOT sqrt(r^2+eps^2)
 //
-// The pair sum is evaluated as -G/2 * sum_i m_i * phi_i with phi_i = sum_{j != i} m_j / (|r_ij| + eps), on the
-// same TMA-fed j-tile ring as the force kernel. Per interaction: 3 FADD2 + 3 FMUL2/FFMA2 (r^2) + MUFU.SQRT +
-// FADD2 + MUFU.RCP + FFMA2, so this kernel is MUFU-bound (2 MUFU per interaction), and it is kept apart from the
-// force kernel for that reason. The self term is masked by index (the reference masks the diagonal with +inf,
-// simulation.py:107-108); distinct coincident bodies contribute m_i m_j / eps exactly as there.
+// The pair sum is evaluated as -G * sum_i m_i * phi_i with phi_i = sum_{j > i} m_j / (|r_ij| + eps) (the upper
+// triangle, as simulation.py:113), on the same TMA-fed j-tile ring as the force kernel; j tiles that lie entirely
+// below a CTA's i-bodies are skipped, so only half of the N^2 pairs are evaluated.
+// Per interaction: 3 FADD2 + 3 FMUL2/FFMA2 (r^2) + MUFU.SQRT + FADD2 + MUFU.RCP + FFMA2, so this kernel is MUFU-bound
+// (2 MUFU per interaction), and it is kept apart from the force kernel for that reason. Pairs with j <= i are masked by index (the reference masks the diagonal with +inf and
+// keeps triu(1), simulation.py:107-113); distinct coincident bodies contribute m_i m_j / eps exactly as there.
 // Tile sums are FP32, everything across tiles / threads / CTAs is FP64, and every cross-CTA sum is taken in a
 // fixed order, so the result is deterministic and closer to the exact value than the reference's FP32 reduction.
 #pragma once
@@ -66,15 +67,19 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
     const int j0 = min(int(blockIdx.y) * per, nj);
     const int j1 = min(int(blockIdx.y + 1) * per, nj);
 
+    // upper triangle: the smallest global i of this CTA bounds the j range from below (rounded down to a tile so
+    // that TMA sources stay 16-byte aligned and tiles line up between CTAs)
+    const int tile_base = blockIdx.x * kTileI;
+    const int i_min = p.i_begin + min(tile_base, p.i_count - 1);
+    const int j_lo = max(j0, (i_min / kTileJ) * kTileJ);
     Ring ring;
-    ring.attach(smem_raw, p.bodies + j0, j1 - j0);
+    ring.attach(smem_raw, p.bodies + min(j_lo, j1), max(j1 - j_lo, 0));
     const int ntiles = ring.num_tiles();
     if (tid == 0) ring.init_barriers();
     __syncthreads();
     if (tid == 0)
         for (int t = 0; t < min(kEnergyLookahead, ntiles); ++t) ring.issue(t);
 
-    const int tile_base = blockIdx.x * kTileI;
     float4 me[kI];
     int gi[kI];
     bool valid[kI];
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
 
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + kEnergyLookahead < ntiles) ring.issue(t + kEnergyLookahead);
-        const int jt = j0 + t * kTileJ;
+        const int jt = j_lo + t * kTileJ;
         const int count = ring.tile_count(t);
         const float4* __restrict__ tj = ring.tile(t);
         float2 acc[kPairs];
@@ -122,8 +127,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
                 r2 = __ffma2_rn(dz, dz, r2);
                 const float2 d = __fadd2_rn(make_float2(sqrt_approx(r2.x), sqrt_approx(r2.y)), eps);
                 float2 inv = make_float2(rcp_approx(d.x), rcp_approx(d.y));
-                if (jg == gi[2 * q]) inv.x = 0.f;
-                if (jg == gi[2 * q + 1]) inv.y = 0.f;
+                if (jg <= gi[2 * q]) inv.x = 0.f;
+                if (jg <= gi[2 * q + 1]) inv.y = 0.f;
                 acc[q] = __ffma2_rn(bm, inv, acc[q]);
             }
         }
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
     if (tid == 0) p.cta_partial[size_t(blockIdx.y) * gridDim.x + blockIdx.x] = total;
 }
 
-// Single-CTA finish: u = -G/2 * sum(cta_partial) and k = sum 0.5 m v^2, both in fixed order.
+// Single-CTA finish: u = -G * sum(cta_partial) and k = sum 0.5 m v^2, both in fixed order.
 struct EnergyFinishParams {
     const double* cta_partial;
     int n_partials;
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(1024) energy_finish_kernel(const EnergyFinishP
     }
     const double k_tot = block_sum<1024>(k, s_red);
     if (threadIdx.x == 0) {
-        p.out_uk[0] = -0.5 * double(p.g) * u_tot;
+        p.out_uk[0] = -double(p.g) * u_tot;
         p.out_uk[1] = k_tot;
     }
 }

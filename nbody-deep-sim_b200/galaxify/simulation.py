@@ -179,12 +179,14 @@ class BaseSimulator:
         State k describes the system after step k+1; the initial state is not recorded; `step` is 0-based.
         With record_every > 1 (an addition) only every record_every-th step is recorded.
         """
-        if self._integrator is None:
-            self.step()  # raises NotImplementedError, like the reference on the first loop iteration
         if record_every < 1:
             raise ValueError("record_every must be >= 1")
         states: list[SimulationState] = []
-        if steps <= 0 or self.n == 0:
+        if steps <= 0:
+            return states
+        if self._integrator is None:
+            self.step()  # raises NotImplementedError, like the reference on the first loop iteration
+        if self.n == 0:
             return states
         n = self.n
         chunk_slots = max(1, TRAJ_CHUNK_BYTES // (36 * n))
