@@ -132,7 +132,7 @@ def cpu_baseline(pos, mass, rows):
             "host_cpus": os.cpu_count()}
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, json_out):
     if rank != 0:
         return
     n = args.n_bodies
@@ -149,13 +149,13 @@ def run_reference_arm(args, rank):
             "sample": f"each step = oracle port of simulation.py:71-89 for {rows} i-bodies x all {n:,} j-bodies "
                       f"(the full step is {n // rows}x that); unmodified reference cannot allocate this N",
             "host_cpus": os.cpu_count()}
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    print(file=json_out, flush=True, *[json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
                       "ms_per_full_step_extrapolated": secs / args.steps * 1e3 * (n / rows),
                       "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(n, args.gpus),
                       "cpu_baseline": base,
-                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
 
 
 # --------------------------------------------------------------------------------------------------- GPU arm
@@ -300,9 +300,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, json_out)
         return
 
     if not torch.cuda.is_available():
@@ -332,7 +335,7 @@ def main():
         if res["kernel_ms"]:
             k_ms = statistics.mean(res["kernel_ms"])
             achieved = FLOPS_PER_INTERACTION * res["interactions_per_kernel"] / (k_ms * 1e-3) / 1e12
-            kernel = "force_kernel<2,8,2,1024> (1 launch per step)"
+            kernel = "force_kernel<2,16,1,1024> (1 launch per step)"
         else:  # sharded: several force launches per step; report the whole-step rate per GPU
             k_ms = res["total_ms"] / args.steps
             achieved = FLOPS_PER_INTERACTION * n * n / world / (k_ms * 1e-3) / 1e12
@@ -350,7 +353,7 @@ def main():
                             "issue_bound_frac": 20.0 / 24.0}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(res["pos"], res["mass"], args.cpu_rows)
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         import torch.distributed as dist
 

@@ -83,14 +83,16 @@ int current_device_info(const DeviceInfo** out) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Kernel shapes. LARGE: 256 threads x 4 i-bodies, 2 CTAs/SM, 1024-body j tiles. SMALL: 128 threads x 2 i-bodies,
-// 4 CTAs/SM, 512-body j tiles (more, smaller CTAs so that mid-size N still fills 148 SMs).
+// Kernel shapes (picked on the GPU with tools/tune_force.cu, profiles/r1_tune_force_variants*.log).
+// LARGE: 512 threads x 4 i-bodies, 1 CTA/SM, 1024-body j tiles, unroll 4 (72.0% of the FP32 roofline in isolation).
+// SMALL: 128 threads x 2 i-bodies, 4 CTAs/SM, 512-body j tiles, unroll 8 (68.6%): more, smaller CTAs so that mid-size
+// N still fills 148 SMs.
 struct Shape {
-    int pairs, warps, min_blocks, tile_j;
+    int pairs, warps, min_blocks, tile_j, unroll;
     int tile_i() const { return warps * 32 * pairs * 2; }
 };
-constexpr Shape kLarge{2, 8, 2, 1024};
-constexpr Shape kSmall{1, 4, 4, 512};
+constexpr Shape kLarge{2, 16, 1, 1024, 4};
+constexpr Shape kSmall{1, 4, 4, 512, 8};
 constexpr int kMaxSplits = 16;
 constexpr int kPlanSms = 148;  // B200. Plans (and so workspace sizes) are a pure function of the problem size.
 
@@ -98,15 +100,12 @@ struct Plan {
     bool large;
     int i_tiles;
     int splits;  // per part
-    Shape shape() const { return large ? kLarge : kSmall; }
 };
 
-Plan plan_force(int n_local, int j_len) {
-    const int sms = kPlanSms;
-    Plan pl;
-    pl.large = n_local >= kLarge.tile_i() * sms;
-    const Shape sh = pl.shape();
-    pl.i_tiles = (n_local + sh.tile_i() - 1) / sh.tile_i();
+// Best split count of one shape: the fewest splits whose CTA count wastes <= 3% of the last wave (more splits only
+// add partial traffic), else the least wasteful.
+static void plan_shape(const Shape& sh, int n_local, int j_len, int sms, int* i_tiles, int* splits, double* waste_out) {
+    *i_tiles = (n_local + sh.tile_i() - 1) / sh.tile_i();
     const int slots = sms * sh.min_blocks;
     int max_splits = j_len / (2 * sh.tile_j);
     if (max_splits < 1) max_splits = 1;
@@ -114,16 +113,31 @@ Plan plan_force(int n_local, int j_len) {
     int best = 1;
     double best_waste = 1e30;
     for (int s = 1; s <= max_splits; ++s) {
-        const double ctas = double(pl.i_tiles) * s;
+        const double ctas = double(*i_tiles) * s;
         const double waves = ctas / slots;
         const double waste = double((long long)((ctas + slots - 1) / slots)) / waves;
         if (waste < best_waste - 1e-9) {
             best_waste = waste;
             best = s;
         }
-        if (waste <= 1.03) break;  // good enough: prefer few splits
+        if (waste <= 1.03) break;
     }
-    pl.splits = best;
+    *splits = best;
+    *waste_out = best_waste;
+}
+
+// LARGE runs ~5% faster per interaction than SMALL (measured in tools/tune_force.cu), so it is taken whenever it
+// fills the machine about as well.
+Plan plan_force(int n_local, int j_len) {
+    const int sms = kPlanSms;
+    int tiles_l, splits_l, tiles_s, splits_s;
+    double waste_l, waste_s;
+    plan_shape(kLarge, n_local, j_len, sms, &tiles_l, &splits_l, &waste_l);
+    plan_shape(kSmall, n_local, j_len, sms, &tiles_s, &splits_s, &waste_s);
+    Plan pl;
+    pl.large = waste_l <= waste_s * 1.05;
+    pl.i_tiles = pl.large ? tiles_l : tiles_s;
+    pl.splits = pl.large ? splits_l : splits_s;
     return pl;
 }
 
@@ -177,16 +191,16 @@ int set_smem(K kernel, size_t bytes) {
     return NBODY_OK;
 }
 
-template <int kPairs, int kWarps, int kMinBlocks, int kTileJ>
+template <int kPairs, int kWarps, int kMinBlocks, int kTileJ, int kUnroll>
 int launch_force_shape(const ForceParams& p, int i_tiles, int splits, bool exact_diag, cudaStream_t stream) {
     const size_t smem = TileRing<kTileJ, kStages, kWarps>::smem_bytes();
     const dim3 grid(i_tiles, splits), block(kWarps * 32);
     if (exact_diag) {
-        auto k = force_kernel<kPairs, kWarps, kMinBlocks, kTileJ, true>;
+        auto k = force_kernel<kPairs, kWarps, kMinBlocks, kTileJ, true, kUnroll>;
         if (int st = set_smem(k, smem)) return st;
         k<<<grid, block, smem, stream>>>(p);
     } else {
-        auto k = force_kernel<kPairs, kWarps, kMinBlocks, kTileJ, false>;
+        auto k = force_kernel<kPairs, kWarps, kMinBlocks, kTileJ, false, kUnroll>;
         if (int st = set_smem(k, smem)) return st;
         k<<<grid, block, smem, stream>>>(p);
     }
@@ -198,10 +212,10 @@ int launch_force(const Plan& pl, const ForceParams& p, cudaStream_t stream) {
     // softening^2 below the smallest normal float is flushed by MUFU.RSQ: take the index-masked variant.
     const bool exact_diag = !(p.eps2 >= 1.17549435e-38f);
     if (pl.large)
-        return launch_force_shape<kLarge.pairs, kLarge.warps, kLarge.min_blocks, kLarge.tile_j>(p, pl.i_tiles, pl.splits,
-                                                                                              exact_diag, stream);
-    return launch_force_shape<kSmall.pairs, kSmall.warps, kSmall.min_blocks, kSmall.tile_j>(p, pl.i_tiles, pl.splits,
-                                                                                          exact_diag, stream);
+        return launch_force_shape<kLarge.pairs, kLarge.warps, kLarge.min_blocks, kLarge.tile_j, kLarge.unroll>(
+            p, pl.i_tiles, pl.splits, exact_diag, stream);
+    return launch_force_shape<kSmall.pairs, kSmall.warps, kSmall.min_blocks, kSmall.tile_j, kSmall.unroll>(
+        p, pl.i_tiles, pl.splits, exact_diag, stream);
 }
 
 int launch_prep(const PrepParams& p, cudaStream_t stream) {
@@ -274,6 +288,16 @@ uint64_t nbody_launch_count(void) { return g_launches.load(std::memory_order_rel
 size_t nbody_workspace_bytes(int n_local, int n_total) {
     if (n_local < 1 || n_total < n_local) return 0;
     return workspace_bytes_impl(n_local, n_total, 1, true);
+}
+
+int nbody_plan_f32(int n_local, int j_len, int* shape_large, int* i_tiles, int* splits) {
+    if (n_local < 1 || j_len < 1 || !shape_large || !i_tiles || !splits)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "plan: bad argument");
+    const Plan pl = plan_force(n_local, j_len);
+    *shape_large = pl.large ? 1 : 0;
+    *i_tiles = pl.i_tiles;
+    *splits = pl.splits;
+    return NBODY_OK;
 }
 
 size_t nbody_shard_workspace_bytes(int n_local, int n_total, int n_parts) {

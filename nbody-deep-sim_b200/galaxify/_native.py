@@ -39,6 +39,7 @@ SIGNATURES = {
     "nbody_last_error": (c_char_p, []),
     "nbody_launch_count": (c_uint64, []),
     "nbody_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nbody_plan_f32": (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "nbody_accel_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "nbody_integrate_f32": (
         c_int,

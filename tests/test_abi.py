@@ -21,7 +21,7 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol():
     lib = _native.lib()
     names = declared_symbols()
-    assert len(names) >= 18
+    assert len(names) >= 19
     for name in names:
         assert hasattr(lib, name), name
     assert sorted(_native.SIGNATURES) == names  # the binding covers exactly the header
@@ -46,6 +46,25 @@ def test_workspace_bytes_is_pure_and_monotone():
     assert lib.nbody_shard_workspace_bytes(1 << 17, 1 << 20, 8) > 0
     assert lib.nbody_shard_workspace_bytes(1 << 17, 1 << 20, 0) == 0
     assert lib.nbody_batched_max_n() == 2048
+
+
+def test_launch_plan_fills_the_machine():
+    """Plans are pure functions of the sizes; every plan's CTA count should waste little of its last wave."""
+    lib = _native.lib()
+    for n, j in ((1 << 20, 1 << 20), (262144, 262144), (131072, 349525), (65536, 65536), (16384, 16384), (1000, 1000)):
+        large, tiles, splits = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.nbody_plan_f32(n, j, ctypes.byref(large), ctypes.byref(tiles), ctypes.byref(splits)) == 0
+        tile_i = 2048 if large.value else 256
+        slots = 148 * (1 if large.value else 4)
+        assert tiles.value == -(-n // tile_i) and 1 <= splits.value <= 16
+        ctas = tiles.value * splits.value
+        if n >= 16384:
+            assert -(-ctas // slots) * slots / ctas <= 1.16, (n, large.value, tiles.value, splits.value)
+    # the headline and the 8-GPU shard both take the 4-bodies-per-thread shape
+    for n, j in ((1 << 20, 1 << 20), (131072, 349525)):
+        assert lib.nbody_plan_f32(n, j, ctypes.byref(large), ctypes.byref(tiles), ctypes.byref(splits)) == 0
+        assert large.value == 1
+    assert lib.nbody_plan_f32(0, 5, ctypes.byref(large), ctypes.byref(tiles), ctypes.byref(splits)) == -1
 
 
 def test_argument_errors_are_reported_without_touching_a_device():

@@ -71,25 +71,20 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(d, h.data(), sizeof(float4) * n_j, cudaMemcpyHostToDevice));
 #define RUN(P, W, B, T, U) run<P, W, B, T, U>("<" #P "," #W "," #B "," #T ",u" #U ">", d, n_j, acc, sms)
     RUN(2, 8, 2, 1024, 4);
-    RUN(2, 8, 2, 1024, 2);
-    RUN(2, 8, 2, 1024, 8);
-    RUN(2, 8, 2, 1024, 1);
-    RUN(2, 4, 4, 512, 4);
+    RUN(2, 16, 1, 1024, 2);
     RUN(2, 16, 1, 1024, 4);
-    RUN(1, 4, 4, 512, 4);
-    RUN(1, 4, 4, 512, 8);
-    RUN(1, 4, 8, 512, 4);
-    RUN(1, 4, 8, 512, 8);
-    RUN(1, 8, 4, 512, 4);
-    RUN(1, 8, 4, 512, 8);
-    RUN(1, 4, 6, 512, 4);
-    RUN(1, 4, 6, 512, 8);
-    RUN(3, 4, 3, 512, 2);
-    RUN(3, 4, 3, 512, 4);
-    RUN(3, 8, 1, 1024, 4);
-    RUN(4, 8, 1, 1024, 2);
+    RUN(2, 16, 1, 1024, 8);
+    RUN(2, 16, 1, 2048, 4);
+    RUN(2, 16, 1, 512, 4);
+    RUN(2, 12, 1, 1024, 4);
+    RUN(2, 12, 1, 1024, 8);
+    RUN(2, 20, 1, 1024, 4);
+    RUN(2, 24, 1, 1024, 4);
+    RUN(1, 32, 1, 1024, 4);
+    RUN(1, 32, 1, 1024, 8);
+    RUN(1, 16, 2, 1024, 8);
+    RUN(3, 12, 1, 1024, 4);
+    RUN(3, 10, 1, 1024, 4);
     RUN(4, 8, 1, 1024, 4);
-    RUN(4, 4, 2, 1024, 2);
-    RUN(4, 4, 2, 1024, 4);
     return 0;
 }
