@@ -4,17 +4,22 @@
 // system evolves exactly as LeapFrogSimulator.step / EulerSimulator.step (src/galaxify/simulation.py:153-187)
 // would evolve it alone (same separately-rounded multiply/add updates), with the force of simulation.py:71-89.
 //
-// One CTA per system. The (x,y,z,m) bodies live in shared memory (double-buffered, so one __syncthreads per step),
-// every thread keeps the position, velocity and acceleration of its 2*kPairs bodies in registers across steps,
-// and the j loop reads shared memory with broadcast LDS.128 and runs the same packed-FP32 inner loop as the
-// large-N force kernel. Global memory is touched only to load the initial state and to record trajectory slots.
+// One thread-block cluster (1, 2 or 4 CTAs of 32..128 threads) per system. The (x,y,z,m) bodies live in shared memory
+// (double-buffered, one cluster barrier per step), every thread keeps the position, velocity and acceleration of its
+// 2*kPairs bodies in registers across steps, and the j loop reads shared memory with broadcast LDS.128 and runs the
+// same packed-FP32 inner loop as the large-N force kernel. Global memory is touched only to load the initial state
+// and to record trajectory slots.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "async_copy.cuh"
 #include "force.cuh"
 
 namespace nb {
 
-constexpr int kBatchedThreads = 256;
+constexpr int kBatchedMaxThreads = 128;
+constexpr int kBatchedMaxPairs = 2;
+constexpr int kBatchedMaxCluster = 4;
 
 struct BatchedParams {
     int n;  // bodies per system
@@ -76,28 +81,44 @@ __device__ __forceinline__ void batched_force(const float4* __restrict__ bodies,
     }
 }
 
-template <int kPairs, bool kExactDiag>
+// One thread-block CLUSTER per system: the system's i-bodies are split evenly over the cluster's CTAs (so that the
+// schedulable unit is a fraction of a system and 512 systems spread evenly over 148 SMs), every CTA keeps a full copy
+// of the (x,y,z,m) array in its own shared memory, and after the drift each CTA stores its updated bodies into every
+// copy through distributed shared memory; one cluster barrier per step replaces the __syncthreads.
+template <int kPairs, int kBatchedThreads, bool kExactDiag>
 __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedParams p) {
+    namespace cg = cooperative_groups;
     constexpr int kI = 2 * kPairs;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* buf0 = reinterpret_cast<float4*>(smem_raw);
     float4* buf1 = buf0 + p.n;
 
-    const int sys = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = int(cluster.num_blocks());
+    const int crank = int(cluster.block_rank());
+    const int sys = blockIdx.x / csize;
     const int tid = threadIdx.x;
+    const int per = (p.n + csize - 1) / csize;  // i-bodies of one CTA
+    const int i_lo = crank * per;
+    const int i_hi = min(p.n, i_lo + per);
+
     const size_t base3 = size_t(sys) * p.n * 3;
     const float* mass = p.mass + size_t(sys) * p.n;
     float* gpos = p.pos + base3;
     float* gvel = p.vel + base3;
     float* gacc = p.acc + base3;
 
+    // every CTA loads the whole system into its own copy
+    for (int j = tid; j < p.n; j += kBatchedThreads)
+        buf0[j] = make_float4(gpos[3 * j], gpos[3 * j + 1], gpos[3 * j + 2], mass[j]);
+
     int idx[kI];
     bool valid[kI];
     float x[kI][3], v[kI][3], a[kI][3], m[kI], sum[kI][3];
 #pragma unroll
     for (int k = 0; k < kI; ++k) {
-        const int i = k * kBatchedThreads + tid;
-        valid[k] = i < p.n;
+        const int i = i_lo + k * kBatchedThreads + tid;
+        valid[k] = i < i_hi;
         idx[k] = min(i, p.n - 1);
         m[k] = mass[idx[k]];
 #pragma unroll
@@ -106,7 +127,6 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
             v[k][c] = gvel[3 * idx[k] + c];
             a[k][c] = (p.mode == MODE_LEAPFROG) ? gacc[3 * idx[k] + c] : 0.f;
         }
-        if (valid[k]) buf0[idx[k]] = make_float4(x[k][0], x[k][1], x[k][2], m[k]);
     }
     __syncthreads();
 
@@ -122,20 +142,29 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
         return;
     }
 
+    // publishes this thread's drifted bodies into every CTA's copy of `dst`
+    auto publish = [&](float4* dst) {
+#pragma unroll
+        for (int k = 0; k < kI; ++k) {
+            if (!valid[k]) continue;
+            const float4 b = make_float4(x[k][0], x[k][1], x[k][2], m[k]);
+            for (int r = 0; r < csize; ++r) cluster.map_shared_rank(dst, r)[idx[k]] = b;
+        }
+    };
+
     const size_t plane = size_t(p.n_systems) * p.n * 3;
     for (int s = 0; s < p.steps; ++s) {
         if (p.mode == MODE_LEAPFROG) {
             // half-kick + drift (simulation.py:164-166), publish the drifted bodies, then force + closing half-kick
 #pragma unroll
-            for (int k = 0; k < kI; ++k) {
+            for (int k = 0; k < kI; ++k)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     v[k][c] = __fadd_rn(v[k][c], __fmul_rn(p.half_dt, a[k][c]));
                     x[k][c] = __fadd_rn(x[k][c], __fmul_rn(p.dt, v[k][c]));
                 }
-                if (valid[k]) nxt[idx[k]] = make_float4(x[k][0], x[k][1], x[k][2], m[k]);
-            }
-            __syncthreads();
+            publish(nxt);
+            cluster.sync();
             batched_force<kPairs, kExactDiag>(nxt, p.n, p.eps2, x, idx, sum);
 #pragma unroll
             for (int k = 0; k < kI; ++k)
@@ -148,16 +177,15 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
             // force at the current positions, then v += dt*a ; x += dt*v (simulation.py:183-187)
             batched_force<kPairs, kExactDiag>(cur, p.n, p.eps2, x, idx, sum);
 #pragma unroll
-            for (int k = 0; k < kI; ++k) {
+            for (int k = 0; k < kI; ++k)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     a[k][c] = __fmul_rn(p.g, sum[k][c]);
                     v[k][c] = __fadd_rn(v[k][c], __fmul_rn(p.dt, a[k][c]));
                     x[k][c] = __fadd_rn(x[k][c], __fmul_rn(p.dt, v[k][c]));
                 }
-                if (valid[k]) nxt[idx[k]] = make_float4(x[k][0], x[k][1], x[k][2], m[k]);
-            }
-            __syncthreads();
+            publish(nxt);
+            cluster.sync();
         }
         float4* tmp = cur;
         cur = nxt;
@@ -181,6 +209,7 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
             store3(gvel, idx[k], v[k][0], v[k][1], v[k][2]);
             store3(gacc, idx[k], a[k][0], a[k][1], a[k][2]);
         }
+    cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
 }  // namespace nb

@@ -500,8 +500,36 @@ int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_nex
 
 // ------------------------------------------------------------------------------------------------ batched path
 
-int nbody_batched_max_n(void) { return kBatchedThreads * 2 * 4; }
+int nbody_batched_max_n(void) { return kBatchedMaxThreads * 2 * kBatchedMaxPairs * kBatchedMaxCluster; }
 
+}  // extern "C" (templates need C++ linkage)
+
+namespace {
+template <int kPairs, int kThreads>
+int batched_launch_shape(const BatchedParams& p, int csize, bool exact, cudaStream_t stream) {
+    const size_t smem = size_t(2) * p.n * sizeof(float4);
+    auto kernel = exact ? batched_kernel<kPairs, kThreads, true> : batched_kernel<kPairs, kThreads, false>;
+    if (int st = set_smem(kernel, smem)) return st;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(p.n_systems) * csize);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail(NBODY_ERR_CUDA, "batched launch failed: %s", cudaGetErrorString(e));
+    return NBODY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// Shape for systems of n bodies: a single CTA of 32/64/128 threads (2 bodies per thread) up to 256 bodies, then
+// clusters of 2 and 4 CTAs of 128 threads, then 4 bodies per thread.
 static int batched_launch(int mode, float* pos, float* vel, float* acc, const float* mass, int n_systems, int n,
                           float g, float eps2, float dt, float half_dt, int steps, int record_every, float* traj,
                           cudaStream_t stream) {
@@ -511,25 +539,13 @@ static int batched_launch(int mode, float* pos, float* vel, float* acc, const fl
     p.n = n, p.mode = mode, p.steps = steps, p.record_every = record_every > 0 ? record_every : 1;
     p.g = g, p.eps2 = eps2, p.dt = dt, p.half_dt = half_dt;
     p.mass = mass, p.pos = pos, p.vel = vel, p.acc = acc, p.traj = traj, p.n_systems = n_systems;
-    const size_t smem = size_t(2) * n * sizeof(float4);
     const bool exact = !(eps2 >= 1.17549435e-38f);
-    const int pairs = (n + 2 * kBatchedThreads - 1) / (2 * kBatchedThreads);
-#define NB_BATCHED(P, E)                                              \
-    do {                                                              \
-        auto k = batched_kernel<P, E>;                                \
-        if (int st = set_smem(k, smem)) return st;                    \
-        k<<<n_systems, kBatchedThreads, smem, stream>>>(p);           \
-    } while (0)
-    if (pairs <= 1) {
-        if (exact) NB_BATCHED(1, true); else NB_BATCHED(1, false);
-    } else if (pairs == 2) {
-        if (exact) NB_BATCHED(2, true); else NB_BATCHED(2, false);
-    } else {
-        if (exact) NB_BATCHED(4, true); else NB_BATCHED(4, false);
-    }
-#undef NB_BATCHED
-    NB_LAUNCH_CHECK();
-    return NBODY_OK;
+    if (n <= 64) return batched_launch_shape<1, 32>(p, 1, exact, stream);
+    if (n <= 128) return batched_launch_shape<1, 64>(p, 1, exact, stream);
+    if (n <= 256) return batched_launch_shape<1, 128>(p, 1, exact, stream);
+    if (n <= 512) return batched_launch_shape<1, 128>(p, 2, exact, stream);
+    if (n <= 1024) return batched_launch_shape<1, 128>(p, 4, exact, stream);
+    return batched_launch_shape<2, 128>(p, 4, exact, stream);
 }
 
 int nbody_batched_integrate_f32(int integrator, float* pos, float* vel, float* acc, const float* mass,
