@@ -119,6 +119,12 @@ int nbody_batched_integrate_f32(int integrator, float* pos, float* vel, float* a
                                 int record_every, float* traj, void* stream);
 int nbody_batched_accel_f32(const float* pos, const float* mass, float* acc, int n_systems, int n, float g,
                             float eps2, void* stream);
+/* compute_energies (simulation.py:91-115) for every recorded state of a trajectory buffer written by
+ * nbody_batched_integrate_f32 (or by nbody_integrate_f32, which is the n_systems == 1 layout), all states in
+ * parallel. out: device doubles [slot][n_systems][2] = (u_energy, k_energy). n <= nbody_batched_max_n(),
+ * n_slots <= 65535 per call. */
+int nbody_traj_energies_f32(const float* traj, const float* mass, int n_slots, int n_systems, int n, float g,
+                            float eps, double* out, void* stream);
 
 /* ---------------------------------------------------------------- host-buffer path --------------------------- */
 

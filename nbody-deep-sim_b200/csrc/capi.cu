@@ -565,6 +565,25 @@ int nbody_batched_integrate_f32(int integrator, float* pos, float* vel, float* a
                           static_cast<cudaStream_t>(stream_));
 }
 
+int nbody_traj_energies_f32(const float* traj, const float* mass, int n_slots, int n_systems, int n, float g, float eps,
+                            double* out, void* stream_) {
+    if (!traj || !mass || !out) return fail(NBODY_ERR_INVALID_ARGUMENT, "traj_energies: null pointer");
+    if (n_slots < 0 || n_systems < 1 || n < 1)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "traj_energies: n_slots = %d, n_systems = %d, n = %d", n_slots, n_systems, n);
+    if (n > nbody_batched_max_n())
+        return fail(NBODY_ERR_UNSUPPORTED, "traj_energies: n = %d exceeds %d", n, nbody_batched_max_n());
+    if (n_slots == 0) return NBODY_OK;
+    if (n_slots > 65535) return fail(NBODY_ERR_UNSUPPORTED, "traj_energies: more than 65535 slots per call");
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    TrajEnergyParams p{traj, mass, n_systems, n, g, eps, out};
+    const size_t smem = size_t(n) * sizeof(float4);
+    if (int st = set_smem(traj_energy_kernel, smem)) return st;
+    traj_energy_kernel<<<dim3(n_systems, n_slots), kTrajEnergyThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
 int nbody_batched_accel_f32(const float* pos, const float* mass, float* acc, int n_systems, int n, float g,
                             float eps2, void* stream_) {
     if (!pos || !acc || !mass) return fail(NBODY_ERR_INVALID_ARGUMENT, "batched_accel: null pointer");

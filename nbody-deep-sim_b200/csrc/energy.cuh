@@ -178,4 +178,55 @@ __global__ void __launch_bounds__(1024) energy_finish_kernel(const EnergyFinishP
     }
 }
 
+// Energies of every recorded state of a (batched) trajectory buffer, one CTA per (slot, system): the state's bodies
+// go to shared memory, thread t takes rows i = t, t+T, ... of the upper triangle. Same arithmetic as
+// potential_kernel / energy_finish_kernel (simulation.py:91-115). Used for systems that fit one CTA (n <= 2048),
+// where the whole run is one persistent kernel and the energies are evaluated afterwards, all states in parallel.
+struct TrajEnergyParams {
+    const float* traj;  // [slot][3][n_systems][n][3]
+    const float* mass;  // [n_systems][n]
+    int n_systems, n;
+    float g, eps;
+    double* out;  // [slot][n_systems][2]
+};
+
+constexpr int kTrajEnergyThreads = 128;
+
+__global__ void __launch_bounds__(kTrajEnergyThreads) traj_energy_kernel(const TrajEnergyParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* bodies = reinterpret_cast<float4*>(smem_raw);
+    __shared__ double s_red[kTrajEnergyThreads / 32];
+    const int slot = blockIdx.y, sys = blockIdx.x, tid = threadIdx.x;
+    const size_t plane = size_t(p.n_systems) * p.n * 3;
+    const float* pos = p.traj + size_t(slot) * 3 * plane + size_t(sys) * p.n * 3;
+    const float* vel = pos + plane;
+    const float* mass = p.mass + size_t(sys) * p.n;
+    for (int j = tid; j < p.n; j += kTrajEnergyThreads)
+        bodies[j] = make_float4(pos[3 * j], pos[3 * j + 1], pos[3 * j + 2], mass[j]);
+    __syncthreads();
+    double u = 0.0, k = 0.0;
+    for (int i = tid; i < p.n; i += kTrajEnergyThreads) {
+        const float4 me = bodies[i];
+        float phi = 0.f;
+        for (int j = i + 1; j < p.n; ++j) {
+            const float4 b = bodies[j];
+            const float dx = b.x - me.x, dy = b.y - me.y, dz = b.z - me.z;
+            const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+            phi = __fmaf_rn(b.w, rcp_approx(sqrt_approx(r2) + p.eps), phi);
+        }
+        u += double(me.w) * double(phi);
+        const float vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+        const float v2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+        k += double(__fmul_rn(__fmul_rn(0.5f, me.w), v2));
+    }
+    const double u_tot = block_sum<kTrajEnergyThreads>(u, s_red);
+    __syncthreads();
+    const double k_tot = block_sum<kTrajEnergyThreads>(k, s_red);
+    if (tid == 0) {
+        double* o = p.out + (size_t(slot) * p.n_systems + sys) * 2;
+        o[0] = -double(p.g) * u_tot;
+        o[1] = k_tot;
+    }
+}
+
 }  // namespace nb

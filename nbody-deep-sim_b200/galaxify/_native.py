@@ -67,6 +67,7 @@ SIGNATURES = {
          c_void_p, c_void_p],
     ),
     "nbody_batched_accel_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    "nbody_traj_energies_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "nbody_accel_host_f32": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, POINTER(c_uint64), POINTER(c_uint64)],

@@ -36,8 +36,6 @@ class BatchedSimulator:
             raise ValueError("device debe ser 'cuda', 'cpu' o None")
         if device == "cpu":
             raise RuntimeError("galaxify (B200 engine) has no CPU path")
-        if calc_energy:
-            raise NotImplementedError("batched simulators do not compute energies")
         _native.lib()
         if not torch.cuda.is_available():
             raise RuntimeError("galaxify (B200 engine) needs a CUDA device and found none; there is no CPU fallback")
@@ -84,7 +82,8 @@ class BatchedSimulator:
 
     def run(self, steps: int, record_every: int = 1, to_host: bool = True):
         """Returns the recorded states; tensors have shape (n_systems, n, 3). With to_host=False they stay on the
-        GPU (views of one trajectory buffer) for a consumer that writes them out itself."""
+        GPU (views of one trajectory buffer) for a consumer that writes them out itself. With calc_energy=True,
+        u_energy / k_energy are numpy arrays of shape (n_systems,)."""
         if self._integrator is None:
             raise NotImplementedError("El método step debe ser implementado en la subclase")
         if record_every < 1:
@@ -102,6 +101,14 @@ class BatchedSimulator:
         end.record()
         if not slots:
             return []
+        energies = None
+        if self.calc_energy:
+            energies = torch.empty((slots, self.n_systems, 2), dtype=torch.float64, device=self.device)
+            for lo in range(0, slots, 65535):  # grid.y limit of the energy kernel
+                cnt = min(65535, slots - lo)
+                _native.call("nbody_traj_energies_f32", _ptr(traj[lo]), _ptr(self.masses), cnt, self.n_systems, self.n,
+                             _native.f32(self.g_const), _native.f32(self.softening), _ptr(energies[lo]), self._stream())
+            energies = energies.cpu().numpy()
         if to_host:
             host = torch.empty(traj.shape, dtype=torch.float32, pin_memory=True)
             host.copy_(traj, non_blocking=True)
@@ -111,7 +118,9 @@ class BatchedSimulator:
             end.synchronize()
         per_step = start.elapsed_time(end) * 1e-3 / steps
         return [SimulationState(step=(j + 1) * record_every - 1, step_time=per_step, positions=traj[j, 0],
-                                velocities=traj[j, 1], accelerations=traj[j, 2]) for j in range(slots)]
+                                velocities=traj[j, 1], accelerations=traj[j, 2],
+                                u_energy=energies[j, :, 0] if energies is not None else None,
+                                k_energy=energies[j, :, 1] if energies is not None else None) for j in range(slots)]
 
 
 class BatchedLeapFrogSimulator(BatchedSimulator):

@@ -11,7 +11,8 @@ What differs, on purpose:
   * `run()` executes every step inside one C call (integrator fused into the force kernel, trajectory written to a
     device buffer, one bulk device->host copy per chunk) instead of a Python loop with three `.cpu()` copies per
     step (simulation.py:126-146). `step_time` is the step's device time from CUDA events; the reference stores an
-    unsynchronised wall-clock (simulation.py:127-129).
+    unsynchronised wall-clock (simulation.py:127-129); on the persistent small-system path it is the mean over the
+    call, because the steps never leave the kernel.
   * Optional, additive keywords that the reference does not have: `run(steps, record_every=1)`.
 """
 
@@ -27,6 +28,11 @@ from . import _native
 
 # Upper bound of one trajectory chunk on the device (and of its pinned host mirror).
 TRAJ_CHUNK_BYTES = 2 << 30
+# Systems up to this many bodies are stepped by the persistent one-cluster-per-system kernel (csrc/batched.cuh): all
+# steps of a run() in ONE launch, energies of the recorded states evaluated afterwards, all states in parallel. Above
+# it one fused force/integrator launch per step uses the whole GPU (csrc/force.cuh). The dataset-generation sizes of
+# the reference's experiments (3..500 bodies, gnn_experiment.py:34) all take the persistent path.
+PERSISTENT_MAX_N = 1024
 
 
 @dataclass
@@ -128,7 +134,30 @@ class BaseSimulator:
     def _stream() -> ctypes.c_void_p:
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def _persistent(self) -> bool:
+        return 0 < self.n <= PERSISTENT_MAX_N
+
+    def _integrate_persistent(self, steps, record_every, traj, energies):
+        """All `steps` in one launch of the batched kernel (one system), then the energies of the recorded slots."""
+        s = self._scalars()
+        with torch.cuda.device(self._device_index):
+            _native.call("nbody_batched_integrate_f32", self._integrator, _ptr(self.positions), _ptr(self.velocities),
+                         _ptr(self.accelerations), _ptr(self.masses), 1, self.n, s["g"], s["eps2"], s["dt"],
+                         s["half_dt"], steps, record_every, _ptr(traj), self._stream())
+            if energies is not None and traj is not None:
+                _native.call("nbody_traj_energies_f32", _ptr(traj), _ptr(self.masses), steps // record_every, 1,
+                             self.n, s["g"], s["eps"], _ptr(energies), self._stream())
+
     def _integrate(self, steps, record_every, traj, energies, step_ms):
+        if self._persistent():
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            self._integrate_persistent(steps, record_every, traj, energies)
+            end.record()
+            if step_ms is not None:  # the steps run inside one kernel: report the mean
+                end.synchronize()
+                step_ms[:] = start.elapsed_time(end) / max(steps, 1)
+            return
         s = self._scalars()
         ws = self._ws()
         with torch.cuda.device(self._device_index):
@@ -151,6 +180,11 @@ class BaseSimulator:
         if self.n == 0:
             return acc
         s = self._scalars()
+        if self._persistent():
+            with torch.cuda.device(self._device_index):
+                _native.call("nbody_batched_accel_f32", _ptr(self.positions), _ptr(self.masses), _ptr(acc), 1, self.n,
+                             s["g"], s["eps2"], self._stream())
+            return acc
         ws = self._ws()
         with torch.cuda.device(self._device_index):
             _native.call("nbody_accel_f32", _ptr(self.positions), _ptr(self.masses), _ptr(acc), self.n, s["g"], s["eps2"],
@@ -189,7 +223,7 @@ class BaseSimulator:
         if self.n == 0:
             return states
         n = self.n
-        chunk_slots = max(1, TRAJ_CHUNK_BYTES // (36 * n))
+        chunk_slots = max(1, min(TRAJ_CHUNK_BYTES // (36 * n), 65535))
         chunk_steps = chunk_slots * record_every
         copy_stream = torch.cuda.Stream(device=self.device)
         # fresh tensor, as the reference rebinds self.accelerations every step (simulation.py:168)

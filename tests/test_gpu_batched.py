@@ -77,6 +77,23 @@ def test_batched_zero_softening_and_step():
     assert np.abs(b.positions[0].cpu().numpy() - g["pos"][-1]).max() <= 1e-6 * np.abs(g["pos"][-1]).max()
 
 
+def test_batched_energies_match_reference_and_single_path():
+    from galaxify import batched, simulation
+
+    g = load_golden("spiral_n500_leapfrog")
+    other = load_golden("disk_n500_leapfrog")
+    b = batched.BatchedLeapFrogSimulator(positions=np.stack([g["ic_pos"], other["ic_pos"]]),
+                                         velocities=np.stack([g["ic_vel"], other["ic_vel"]]),
+                                         masses=np.stack([g["ic_mass"], other["ic_mass"]]), calc_energy=True, **g.sim)
+    states = b.run(100)
+    u = np.array([s.u_energy for s in states])
+    k = np.array([s.k_energy for s in states])
+    assert u.shape == (100, 2)
+    for col, gold in ((0, g), (1, other)):
+        assert np.abs(u[:, col] - gold["u"][:100]).max() <= 1e-5 * np.abs(gold["u"]).max()
+        assert np.abs(k[:, col] - gold["k"][:100]).max() <= 1e-5 * np.abs(gold["k"]).max()
+
+
 def test_shard_systems_partitions():
     from galaxify.batched import shard_systems
 

@@ -18,6 +18,17 @@ TRAJ_RTOL = 1e-6
 ENERGY_RTOL = 1e-5
 
 
+@pytest.fixture(params=["persistent", "tiled"])
+def path(request, monkeypatch):
+    """Systems of <= 1024 bodies normally run in the persistent one-cluster kernel (csrc/batched.cuh); "tiled" forces
+    them through the large-N kernel with the fused integrator epilogue (csrc/force.cuh) so both are pinned."""
+    from galaxify import simulation
+
+    if request.param == "tiled":
+        monkeypatch.setattr(simulation, "PERSISTENT_MAX_N", 0)
+    return request.param
+
+
 def make_sim(g, calc_energy=False):
     from galaxify import simulation
 
@@ -27,7 +38,7 @@ def make_sim(g, calc_energy=False):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_initial_accelerations_match_reference(name):
+def test_initial_accelerations_match_reference(name, path):
     g = load_golden(name)
     sim = make_sim(g)
     acc = sim.accelerations.cpu().numpy()
@@ -37,7 +48,7 @@ def test_initial_accelerations_match_reference(name):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_trajectory_matches_reference(name):
+def test_trajectory_matches_reference(name, path):
     g = load_golden(name)
     sim = make_sim(g)
     states = sim.run(g.steps)
@@ -58,7 +69,7 @@ def test_trajectory_matches_reference(name):
 
 
 @pytest.mark.parametrize("name", ["disk_n1024_leapfrog", "spiral_n500_euler", "disk_n3_leapfrog", "spiral_n25_leapfrog"])
-def test_energies_match_reference(name):
+def test_energies_match_reference(name, path):
     g = load_golden(name)
     sim = make_sim(g, calc_energy=True)
     u0, k0 = sim.compute_energies()
@@ -76,7 +87,7 @@ def test_energies_match_reference(name):
     assert drift <= 1.1 * drift_ref + 1e-6
 
 
-def test_step_by_step_equals_run():
+def test_step_by_step_equals_run(path):
     """step() x k and run(k) walk the same rounding sequence (the fused epilogue re-opens the step like prep does)."""
     g = load_golden("spiral_n500_leapfrog")
     a, b = make_sim(g), make_sim(g)
@@ -107,7 +118,7 @@ def test_accelerations_vs_oracle_ragged_sizes(n):
     assert rel_rows(acc[max(0, n - 300):], want_tail).max() <= ACC_RTOL
 
 
-def test_momentum_drift_no_worse_than_reference():
+def test_momentum_drift_no_worse_than_reference(path):
     g = load_golden("disk_n1024_leapfrog")
     sim = make_sim(g)
     m = g["ic_mass"].astype(np.float64)[:, None]
