@@ -124,6 +124,9 @@ def cpu_sample(pos, mass, rows):
 def cpu_baseline(pos, mass, rows):
     n = len(mass)
     cpu_sample(pos, mass, 32)  # warm torch's thread pool
+    if rows <= 0:  # size the sample for ~12 s of CPU work on this host, from a 64-row probe
+        probe = cpu_sample(pos, mass, 64)
+        rows = int(min(8192, max(256, 64 * 12.0 / probe))) // 32 * 32
     secs = cpu_sample(pos, mass, rows)
     return {"value": rows * n / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"oracle/galaxify_oracle.accelerations (torch CPU restatement of simulation.py:71-89) for the "
@@ -290,7 +293,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--n-bodies", type=int, default=1 << 20)
-    ap.add_argument("--cpu-rows", type=int, default=768, help="i-bodies of the cpu_baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=0,
+                    help="i-bodies of the cpu_baseline sample (0 = sized for ~12 s on this host)")
     ap.add_argument("--cpu-rows-per-step", type=int, default=256, help="i-bodies per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
