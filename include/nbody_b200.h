@@ -106,6 +106,12 @@ int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_nex
                           float* acc, float* vhalf, float g, float eps2, float dt, float half_dt, int do_next,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* This rank's share of compute_energies (simulation.py:91-115): u = -G sum_{i local} m_i sum_{j > i} m_j/(|r_ij|+eps)
+ * over the full body array (pad slots must hold zero masses), k over the local velocities. The caller sums the two
+ * doubles over ranks. Workspace: nbody_shard_workspace_bytes(n_local, n_total, 1) suffices. */
+int nbody_shard_energies_f32(const float* bodies, const float* vel, int n_total, int i_begin, int n_local, float g,
+                             float eps, double* out_uk, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- batched many-small-systems path ------------ */
 
 /* `n_systems` independent systems of `n` bodies each (n <= nbody_batched_max_n()), all stepped `steps` times

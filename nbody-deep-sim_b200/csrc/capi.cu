@@ -498,6 +498,20 @@ int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_nex
     return launch_force(pl, fp, stream);
 }
 
+int nbody_shard_energies_f32(const float* bodies, const float* vel, int n_total, int i_begin, int n_local, float g,
+                             float eps, double* out_uk, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!bodies || !vel || !out_uk || !workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_energies: null pointer");
+    if (n_local < 1 || i_begin < 0 || i_begin + n_local > n_total)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_energies: bad range (i %d+%d, n %d)", i_begin, n_local, n_total);
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    Workspace w = carve(workspace, n_local, n_total, 1, false);
+    if (w.total > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "shard_energies: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    return launch_energy(reinterpret_cast<const float4*>(bodies), vel, n_total, i_begin, n_local, g, eps,
+                         w.energy_partial, out_uk, dev->sms, static_cast<cudaStream_t>(stream_));
+}
+
 // ------------------------------------------------------------------------------------------------ batched path
 
 int nbody_batched_max_n(void) { return kBatchedMaxThreads * 2 * kBatchedMaxPairs * kBatchedMaxCluster; }

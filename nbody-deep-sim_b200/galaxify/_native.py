@@ -60,6 +60,10 @@ SIGNATURES = {
         [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
          c_void_p, c_float, c_float, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p],
     ),
+    "nbody_shard_energies_f32": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
     "nbody_batched_max_n": (c_int, []),
     "nbody_batched_integrate_f32": (
         c_int,

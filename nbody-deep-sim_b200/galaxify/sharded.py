@@ -1,7 +1,8 @@
 """i-sharded large-N simulators: one process per GPU, positions all-gathered every step over NCCL.
 
 An addition with no reference counterpart (the reference is single-device, simulation.py:46-51). The constructor
-keeps the reference's keyword arguments; every rank passes the SAME full arrays and keeps only its slice.
+keeps the reference's keyword arguments (calc_energy defaults to False here); every rank passes the SAME full
+arrays and keeps only its slice. Energies are reduced over ranks with one all-reduce of two doubles.
 
 Layout: the body array (x,y,z,m float4) has world_size slots of `n_pad = ceil(n / world_size)` bodies; rank r owns
 global indices [r*n_pad, r*n_pad + count_r). Padding bodies are never read: each step is a set of j-range "parts",
@@ -56,8 +57,6 @@ class ShardedSimulator:
                  dt: float = 0.01, calc_energy: bool = False, device: str = None, group=None):
         if device is not None and device not in ["cuda", "cpu"]:
             raise ValueError("device debe ser 'cuda', 'cpu' o None")
-        if calc_energy:
-            raise NotImplementedError("sharded simulators do not compute energies yet")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world_size = dist.get_world_size(group)
@@ -84,6 +83,8 @@ class ShardedSimulator:
         self.accelerations = torch.zeros_like(self.positions)
         self._vhalf = torch.zeros_like(self.positions)
         self._bodies = [torch.zeros((self.world_size * self.n_pad, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+        for b in self._bodies:  # pad entries of the own slot: massless and far away, so that no kernel that sweeps the
+            b[self.i_begin + self.n_local : self.i_begin + self.n_pad, :3] = 1e18  # whole array can divide by zero
         self._parts = step_parts(self.rank, self.n_pad, self.counts)
         self._workspace = self._alloc_workspace()
         self.launches_per_step = len(self._parts)
@@ -129,6 +130,28 @@ class ShardedSimulator:
                      _ptr(self._vhalf), s["g"], s["eps2"], s["dt"], s["half_dt"], do_next, _ptr(ws), ws.numel(),
                      self._stream())
 
+    def _local_energies(self, bodies):
+        """This rank's (u, k) partial sums as a device tensor of two doubles."""
+        out = torch.empty(2, dtype=torch.float64, device=self.device)
+        ws = self._workspace
+        _native.call("nbody_shard_energies_f32", _ptr(bodies), _ptr(self.velocities), self.world_size * self.n_pad,
+                     self.i_begin, self.n_local, _native.f32(self.g_const), _native.f32(self.softening), _ptr(out),
+                     _ptr(ws), ws.numel(), self._stream())
+        return out
+
+    def _energies_of(self, bodies):
+        out = self._local_energies(bodies)
+        dist.all_reduce(out, group=self.group)
+        u, k = out.tolist()
+        return u, k
+
+    def compute_energies(self):
+        """(u_energy, k_energy) of the whole system (simulation.py:91-115), identical on every rank."""
+        bodies = self._bodies[0]
+        self._prepare(0, bodies)
+        self._gather(bodies).wait()
+        return self._energies_of(bodies)
+
     def _gather(self, bodies):
         """In-place all-gather of every rank's slot; returns the async work handle."""
         mine = bodies[self.i_begin : self.i_begin + self.n_pad]
@@ -158,7 +181,7 @@ class ShardedSimulator:
                 # leapfrog: the drift of the NEXT step already went into self.positions; state s sits in the
                 # buffer this step consumed. Euler: state s is what the epilogue just wrote.
                 src = self._bodies[cur] if integ == _native.INTEGRATOR_LEAPFROG else self._bodies[cur ^ 1]
-                on_state(s, src[self.i_begin : self.i_begin + self.n_local, :3])
+                on_state(s, src)
             cur ^= 1
 
     def step(self):
@@ -172,11 +195,18 @@ class ShardedSimulator:
             raise NotImplementedError("El método step debe ser implementado en la subclase")
         states = []
 
-        def record(s, pos_view):
-            if (s + 1) % record_every == 0:
-                states.append(SimulationState(step=s, step_time=float("nan"), positions=pos_view.cpu(),
-                                              velocities=self.velocities.cpu(),
-                                              accelerations=self.accelerations.cpu()))
+        def record(s, bodies):
+            if (s + 1) % record_every:
+                return
+            u = k = None
+            if self.calc_energy:
+                if self._integrator == _native.INTEGRATOR_EULER:  # the epilogue wrote only this rank's slice
+                    self._gather(bodies).wait()
+                u, k = self._energies_of(bodies)
+            states.append(SimulationState(step=s, step_time=float("nan"),
+                                          positions=bodies[self.i_begin : self.i_begin + self.n_local, :3].cpu(),
+                                          velocities=self.velocities.cpu(), accelerations=self.accelerations.cpu(),
+                                          u_energy=u, k_energy=k))
 
         self._advance(steps, record)
         return states

@@ -38,12 +38,14 @@ def _worker(rank, world, port, n, integrator, steps, out_dir):
         pos, vel, mass = galaxies.generate_disk(n_bodies=n, total_mass=1.0, radial_scale=3.0, height_scale=0.3,
                                                 g_const=4.5e-6, black_hole_mass=0.01, seed=n)
         cls = sharded.ShardedLeapFrogSimulator if integrator == "leapfrog" else sharded.ShardedEulerSimulator
-        sim = cls(positions=pos, velocities=vel, masses=mass, g_const=4.5e-6, softening=0.05, dt=1e-4)
+        sim = cls(positions=pos, velocities=vel, masses=mass, g_const=4.5e-6, softening=0.05, dt=1e-4, calc_energy=True)
         acc0 = sim.gather_state()[2].numpy()
+        e0 = sim.compute_energies()
         states = sim.run(steps)
         p, v, a = (t.numpy() for t in sim.gather_state())
         if rank == 0:
-            np.savez(os.path.join(out_dir, "out.npz"), acc0=acc0, pos=p, vel=v, acc=a, n_states=len(states),
+            np.savez(os.path.join(out_dir, "out.npz"), acc0=acc0, pos=p, vel=v, acc=a, n_states=len(states), e0=e0,
+                     e=np.array([[st.u_energy, st.k_energy] for st in states]),
                      first=states[0].positions.numpy(), n_local=sim.n_local)
     finally:
         dist.destroy_process_group()
@@ -57,12 +59,14 @@ def _check(tmp_path, world, n, integrator, steps):
     pos, vel, mass = galaxies.generate_disk(n_bodies=n, total_mass=1.0, radial_scale=3.0, height_scale=0.3,
                                             g_const=4.5e-6, black_hole_mass=0.01, seed=n)
     cls = simulation.LeapFrogSimulator if integrator == "leapfrog" else simulation.EulerSimulator
-    single = cls(positions=pos, velocities=vel, masses=mass, g_const=4.5e-6, softening=0.05, dt=1e-4, calc_energy=False)
+    single = cls(positions=pos, velocities=vel, masses=mass, g_const=4.5e-6, softening=0.05, dt=1e-4, calc_energy=True)
+    np.testing.assert_allclose(z["e0"], single.compute_energies(), rtol=1e-6)
     # two FP32 evaluations with different j-split orders: each is within ~1e-6 of exact, bar is the north-star 1e-5
     err0 = rel_rows(z["acc0"], single.accelerations.cpu().numpy()).max()
     assert err0 <= 5e-6, err0
     ref = single.run(steps)
     assert int(z["n_states"]) == steps
+    np.testing.assert_allclose(z["e"], [[st.u_energy, st.k_energy] for st in ref], rtol=1e-6)
     for key, want in (("pos", ref[-1].positions), ("vel", ref[-1].velocities)):
         want = want.numpy()
         assert np.abs(z[key] - want).max() <= 1e-6 * np.abs(want).max(), key
