@@ -35,21 +35,25 @@ struct BatchedParams {
     int n_systems;
 };
 
+constexpr int kBatchedFold = 32;  // FP32 accumulation run length, as in force.cuh
+
 template <int kPairs, bool kExactDiag>
 __device__ __forceinline__ void batched_force(const float4* __restrict__ bodies, int n, float eps2s,
                                               const float (&x)[2 * kPairs][3], const int (&idx)[2 * kPairs],
                                               float (&sum)[2 * kPairs][3]) {
     float2 nx[kPairs], ny[kPairs], nz[kPairs], ax[kPairs], ay[kPairs], az[kPairs];
+    double tot[2 * kPairs][3];
 #pragma unroll
     for (int q = 0; q < kPairs; ++q) {
         nx[q] = make_float2(-x[2 * q][0], -x[2 * q + 1][0]);
         ny[q] = make_float2(-x[2 * q][1], -x[2 * q + 1][1]);
         nz[q] = make_float2(-x[2 * q][2], -x[2 * q + 1][2]);
-        ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
     }
+#pragma unroll
+    for (int k = 0; k < 2 * kPairs; ++k) tot[k][0] = tot[k][1] = tot[k][2] = 0.0;
     const float2 eps2 = make_float2(eps2s, eps2s);
-#pragma unroll 4
-    for (int j = 0; j < n; ++j) {
+
+    auto interact = [&](int j) {
         const float4 b = bodies[j];
         const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
         const float2 bm = make_float2(b.w, b.w);
@@ -73,12 +77,27 @@ __device__ __forceinline__ void batched_force(const float4* __restrict__ bodies,
             ay[q] = __ffma2_rn(w, dy, ay[q]);
             az[q] = __ffma2_rn(w, dz, az[q]);
         }
+    };
+
+    for (int jb = 0; jb < n; jb += kBatchedFold) {
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
+        if (jb + kBatchedFold <= n) {
+#pragma unroll 8
+            for (int u = 0; u < kBatchedFold; ++u) interact(jb + u);
+        } else {
+            for (int j = jb; j < n; ++j) interact(j);
+        }
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+            tot[2 * q][0] += double(ax[q].x), tot[2 * q][1] += double(ay[q].x), tot[2 * q][2] += double(az[q].x);
+            tot[2 * q + 1][0] += double(ax[q].y), tot[2 * q + 1][1] += double(ay[q].y), tot[2 * q + 1][2] += double(az[q].y);
+        }
     }
 #pragma unroll
-    for (int q = 0; q < kPairs; ++q) {
-        sum[2 * q][0] = ax[q].x, sum[2 * q][1] = ay[q].x, sum[2 * q][2] = az[q].x;
-        sum[2 * q + 1][0] = ax[q].y, sum[2 * q + 1][1] = ay[q].y, sum[2 * q + 1][2] = az[q].y;
-    }
+    for (int k = 0; k < 2 * kPairs; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sum[k][c] = float(tot[k][c]);
 }
 
 // One thread-block CLUSTER per system: the system's i-bodies are split evenly over the cluster's CTAs (so that the

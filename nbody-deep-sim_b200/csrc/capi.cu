@@ -84,14 +84,14 @@ int current_device_info(const DeviceInfo** out) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Kernel shapes (picked on the GPU with tools/tune_force.cu, profiles/r1_tune_force_variants*.log).
-// LARGE: 512 threads x 4 i-bodies, 1 CTA/SM, 1024-body j tiles, unroll 4 (72.0% of the FP32 roofline in isolation).
-// SMALL: 128 threads x 2 i-bodies, 4 CTAs/SM, 512-body j tiles, unroll 8 (68.6%): more, smaller CTAs so that mid-size
-// N still fills 148 SMs.
+// LARGE: 512 threads x 4 i-bodies, 1 CTA/SM, 1024-body j tiles, unroll 8 (68.8% of the FP32 roofline in isolation,
+// with the 32-term accumulation runs that cost ~3%). SMALL: 128 threads x 2 i-bodies, 4 CTAs/SM, 512-body j tiles,
+// unroll 8 (65.1%): more, smaller CTAs so that mid-size N still fills 148 SMs.
 struct Shape {
     int pairs, warps, min_blocks, tile_j, unroll;
     int tile_i() const { return warps * 32 * pairs * 2; }
 };
-constexpr Shape kLarge{2, 16, 1, 1024, 4};
+constexpr Shape kLarge{2, 16, 1, 1024, 8};
 constexpr Shape kSmall{1, 4, 4, 512, 8};
 constexpr int kMaxSplits = 16;
 constexpr int kPlanSms = 148;  // B200. Plans (and so workspace sizes) are a pure function of the problem size.
@@ -144,7 +144,7 @@ Plan plan_force(int n_local, int j_len) {
 struct Workspace {
     float4* bodies[2];
     float* vhalf;
-    float4* partial;
+    double* partial;
     unsigned* counters;
     double* energy_partial;
     double* energy_out;  // 2 doubles, scratch target when the caller wants no energies
@@ -171,7 +171,7 @@ Workspace carve(void* base, int n_local, int n_total, int n_parts, bool own_bodi
     w.partial_stride = int(align_up(size_t(n_local), 32));
     const int j_len = n_total / n_parts > 0 ? n_total / n_parts : 1;
     const int slots = plan_force(n_local, j_len).splits * n_parts;
-    w.partial = static_cast<float4*>(take(size_t(slots) * w.partial_stride * sizeof(float4)));
+    w.partial = static_cast<double*>(take(size_t(slots) * 3 * w.partial_stride * sizeof(double)));
     w.counters = static_cast<unsigned*>(take(kCounterBytes));
     w.energy_partial = static_cast<double*>(take(kEnergyPartialBytes));
     w.energy_out = static_cast<double*>(take(256));

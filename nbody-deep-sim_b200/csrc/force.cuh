@@ -11,9 +11,11 @@
 //   j-bodies (x,y,z,m float4) stream through a kStages-deep shared-memory ring filled kLookahead tiles ahead with
 //   1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); warps release stages with mbarrier arrives, so
 //   there is no CTA-wide barrier in the tile loop and warps may drift up to kStages-kLookahead tiles apart.
-//   Per-tile partial sums are folded into a compensated (Kahan) running total, so the FP32 result stays at the
-//   1e-7 level at N = 1M instead of random-walking to ~1e-5.
-//   With j_splits > 1 every CTA writes its partial to scratch and the last CTA to arrive for an i-tile reduces
+//   Accumulation: FP32 runs of kFold (32) j-bodies, each run folded into an FP64 total (F2F + DADD, off the FMA
+//   pipe). A long plain-FP32 run loses the small terms that follow a large one; for bodies whose forces cancel to a
+//   few 1e-3 of their sum (close to a galaxy's centre) 1024-term runs gave 1e-4 relative error where the reference's
+//   cascade summation gives 1e-6 — 32-term runs bring it to the reference's level (tools/diag_shard_accuracy.py).
+//   With j_splits > 1 every CTA writes its FP64 partial to scratch and the last CTA to arrive for an i-tile reduces
 //   the splits in fixed order (deterministic) and runs the epilogue.
 //
 // Epilogue (per i-body, rounding exactly as the reference: multiply and add rounded separately, no FMA)
@@ -38,7 +40,7 @@ struct ForceParams {
     int i_begin, i_count;  // i range this launch covers (global index of first, count)
     float eps2, g;
     // split-j reduction scratch
-    float4* partial;     // [splits_total][partial_stride]
+    double* partial;     // [splits_total][3][partial_stride] FP64 partial sums
     int partial_stride;  // >= i_count
     int split_offset;    // slot of this launch's split 0 (lets several launches share one reduction)
     int splits_total;    // arrivals per i-tile that trigger the epilogue
@@ -57,13 +59,6 @@ struct ForceParams {
     float* rec_vel;
     float* rec_acc;
 };
-
-__device__ __forceinline__ void kahan_add(float& total, float& comp, float s) {
-    float y = __fsub_rn(s, comp);
-    float t = __fadd_rn(total, y);
-    comp = __fsub_rn(__fsub_rn(t, total), y);
-    total = t;
-}
 
 __device__ __forceinline__ void store3(float* base, int i, float x, float y, float z) {
     if (base) {
@@ -110,7 +105,7 @@ __device__ __forceinline__ void epilogue_body(const ForceParams& p, int li, floa
 
 // kExactDiag: softening^2 underflows FP32 (or is 0), so the self term would be 0*inf. Mask it by index, which is
 // what fill_diagonal_(0) does in the reference (simulation.py:85); two distinct coincident bodies still give NaN there.
-template <int kPairs, int kWarps, int kMinBlocks, int kTileJ, bool kExactDiag, int kUnroll = 4>
+template <int kPairs, int kWarps, int kMinBlocks, int kTileJ, bool kExactDiag, int kUnroll = 4, int kFold = 32>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const ForceParams p) {
     constexpr int kCT = kWarps * 32;  // threads
     constexpr int kI = 2 * kPairs;    // i-bodies per thread
@@ -152,11 +147,11 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const Fo
         nz[q] = make_float2(-me[2 * q].z, -me[2 * q + 1].z);
     }
     float2 ax[kPairs], ay[kPairs], az[kPairs];
-    float tot[kI][3], cmp[kI][3];
+    double tot[kI][3];
 #pragma unroll
     for (int k = 0; k < kI; ++k)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tot[k][c] = cmp[k][c] = 0.f;
+        for (int c = 0; c < 3; ++c) tot[k][c] = 0.0;
 
     const float2 eps2 = make_float2(p.eps2, p.eps2);
 
@@ -165,13 +160,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const Fo
         const int jt = j0 + t * kTileJ;
         const int count = ring.tile_count(t);
         const float4* __restrict__ tj = ring.tile(t);
-#pragma unroll
-        for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
-
         ring.wait(t);
 
-#pragma unroll kUnroll
-        for (int jj = 0; jj < count; ++jj) {
+        // one (i-pair, j) interaction, packed over the pair
+        auto interact = [&](int jj) {
             const float4 b = tj[jj];
             const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
             const float2 bm = make_float2(b.w, b.w);
@@ -196,36 +188,43 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const Fo
                 ay[q] = __ffma2_rn(w, dy, ay[q]);
                 az[q] = __ffma2_rn(w, dz, az[q]);
             }
+        };
+
+        for (int jb = 0; jb < count; jb += kFold) {
+#pragma unroll
+            for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
+            if (jb + kFold <= count) {
+#pragma unroll kUnroll
+                for (int u = 0; u < kFold; ++u) interact(jb + u);
+            } else {
+                for (int jj = jb; jj < count; ++jj) interact(jj);
+            }
+            // fold the run into the FP64 totals
+#pragma unroll
+            for (int q = 0; q < kPairs; ++q) {
+                tot[2 * q][0] += double(ax[q].x), tot[2 * q][1] += double(ay[q].x), tot[2 * q][2] += double(az[q].x);
+                tot[2 * q + 1][0] += double(ax[q].y), tot[2 * q + 1][1] += double(ay[q].y);
+                tot[2 * q + 1][2] += double(az[q].y);
+            }
         }
         ring.release(t);
-
-#pragma unroll
-        for (int q = 0; q < kPairs; ++q) {
-            kahan_add(tot[2 * q][0], cmp[2 * q][0], ax[q].x);
-            kahan_add(tot[2 * q][1], cmp[2 * q][1], ay[q].x);
-            kahan_add(tot[2 * q][2], cmp[2 * q][2], az[q].x);
-            kahan_add(tot[2 * q + 1][0], cmp[2 * q + 1][0], ax[q].y);
-            kahan_add(tot[2 * q + 1][1], cmp[2 * q + 1][1], ay[q].y);
-            kahan_add(tot[2 * q + 1][2], cmp[2 * q + 1][2], az[q].y);
-        }
     }
-#pragma unroll
-    for (int k = 0; k < kI; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) tot[k][c] = __fsub_rn(tot[k][c], cmp[k][c]);
 
     if (p.splits_total == 1) {
 #pragma unroll
         for (int k = 0; k < kI; ++k)
-            if (li[k] < p.i_count) epilogue_body(p, li[k], me[k], tot[k][0], tot[k][1], tot[k][2]);
+            if (li[k] < p.i_count) epilogue_body(p, li[k], me[k], float(tot[k][0]), float(tot[k][1]), float(tot[k][2]));
         return;
     }
 
     // ---- split-j: publish the partial, last arriver reduces in slot order ----
-    float4* mine = p.partial + size_t(p.split_offset + blockIdx.y) * p.partial_stride;
+    double* mine = p.partial + size_t(p.split_offset + blockIdx.y) * 3 * p.partial_stride;
 #pragma unroll
     for (int k = 0; k < kI; ++k)
-        if (li[k] < p.i_count) mine[li[k]] = make_float4(tot[k][0], tot[k][1], tot[k][2], 0.f);
+        if (li[k] < p.i_count) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) mine[size_t(c) * p.partial_stride + li[k]] = tot[k][c];
+        }
     __threadfence();
     compute_barrier<kCT>();
     if (tid == 0) {
@@ -240,10 +239,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const Fo
         if (li[k] >= p.i_count) continue;
         double sx = 0.0, sy = 0.0, sz = 0.0;
         for (int s = 0; s < p.splits_total; ++s) {
-            const float4 v = __ldcg(p.partial + size_t(s) * p.partial_stride + li[k]);
-            sx += double(v.x);
-            sy += double(v.y);
-            sz += double(v.z);
+            const double* src = p.partial + size_t(s) * 3 * p.partial_stride + li[k];
+            sx += __ldcg(src);
+            sy += __ldcg(src + p.partial_stride);
+            sz += __ldcg(src + 2 * size_t(p.partial_stride));
         }
         epilogue_body(p, li[k], me[k], float(sx), float(sy), float(sz));
     }

@@ -27,6 +27,8 @@ def lib():
         h.oracle_accel_f64.restype = None
         h.oracle_accel_f64.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+        h.oracle_accel_cond_f64.restype = None
+        h.oracle_accel_cond_f64.argtypes = h.oracle_accel_f64.argtypes + [ctypes.c_void_p]
         h.oracle_energies_f64.restype = None
         h.oracle_energies_f64.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
@@ -47,6 +49,21 @@ def accelerations_f64(pos, mass, g_const, softening, lo=0, hi=None):
     lib().oracle_accel_f64(p.ctypes.data, m.ctypes.data, n, lo, hi, float(np.float32(g_const)),
                            float(np.float32(softening**2)), out.ctypes.data)
     return out
+
+
+def accelerations_cond_f64(pos, mass, g_const, softening, rows):
+    """(accelerations, kappa) of the bodies whose indices are in `rows`: FP64 accelerations and the condition number
+    sum_j |term_ij| / |a_i| of each body's sum."""
+    p, m = _f32(pos), _f32(mass)
+    n = p.shape[0]
+    acc = np.empty((len(rows), 3), dtype=np.float64)
+    kappa = np.empty(len(rows), dtype=np.float64)
+    one, k1 = np.empty(3, dtype=np.float64), np.empty(1, dtype=np.float64)
+    for r, i in enumerate(rows):
+        lib().oracle_accel_cond_f64(p.ctypes.data, m.ctypes.data, n, int(i), int(i) + 1, float(np.float32(g_const)),
+                                    float(np.float32(softening**2)), one.ctypes.data, k1.ctypes.data)
+        acc[r], kappa[r] = one, k1[0]
+    return acc, kappa
 
 
 def energies_f64(pos, vel, mass, g_const, softening):

@@ -30,6 +30,33 @@ void oracle_accel_f64(const float* pos, const float* mass, int n, int lo, int hi
     }
 }
 
+/* Same sum, plus its condition number kappa_i = sum_j |term_ij| / |a_i| (1-norm of the terms over the norm of the
+ * result): the factor by which per-term rounding errors are amplified for body i. Used to state a principled
+ * tolerance for bodies whose forces nearly cancel (a galaxy's centre), where NO FP32 summation reaches 1e-5. */
+void oracle_accel_cond_f64(const float* pos, const float* mass, int n, int lo, int hi, double g, double eps2, double* out,
+                           double* kappa) {
+#pragma omp parallel for schedule(static)
+    for (int i = lo; i < hi; ++i) {
+        const double xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+        double ax = 0.0, ay = 0.0, az = 0.0, sabs = 0.0;
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            const double dx = pos[3 * j] - xi, dy = pos[3 * j + 1] - yi, dz = pos[3 * j + 2] - zi;
+            const double d2 = dx * dx + dy * dy + dz * dz + eps2;
+            const double w = mass[j] / (d2 * sqrt(d2));
+            ax += w * dx;
+            ay += w * dy;
+            az += w * dz;
+            sabs += w * sqrt(dx * dx + dy * dy + dz * dz);
+        }
+        out[3 * (size_t)(i - lo)] = g * ax;
+        out[3 * (size_t)(i - lo) + 1] = g * ay;
+        out[3 * (size_t)(i - lo) + 2] = g * az;
+        const double norm = sqrt(ax * ax + ay * ay + az * az);
+        kappa[i - lo] = norm > 0.0 ? sabs / norm : INFINITY;
+    }
+}
+
 void oracle_energies_f64(const float* pos, const float* vel, const float* mass, int n, double g, double eps,
                          double* out_uk) {
     double u = 0.0, k = 0.0;

@@ -17,9 +17,9 @@ using namespace nb;
         }                                                                          \
     } while (0)
 
-template <int kPairs, int kWarps, int kMinB, int kTileJ, int kUnroll>
+template <int kPairs, int kWarps, int kMinB, int kTileJ, int kUnroll, int kFold>
 void run(const char* name, const float4* bodies, int n_j, float* acc, int sms) {
-    auto k = force_kernel<kPairs, kWarps, kMinB, kTileJ, false, kUnroll>;
+    auto k = force_kernel<kPairs, kWarps, kMinB, kTileJ, false, kUnroll, kFold>;
     const size_t smem = TileRing<kTileJ, kStages, kWarps>::smem_bytes();
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int occ = 0;
@@ -69,22 +69,18 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d, sizeof(float4) * n_j));
     CK(cudaMalloc(&acc, sizeof(float) * 3 * n_j));
     CK(cudaMemcpy(d, h.data(), sizeof(float4) * n_j, cudaMemcpyHostToDevice));
-#define RUN(P, W, B, T, U) run<P, W, B, T, U>("<" #P "," #W "," #B "," #T ",u" #U ">", d, n_j, acc, sms)
-    RUN(2, 8, 2, 1024, 4);
-    RUN(2, 16, 1, 1024, 2);
-    RUN(2, 16, 1, 1024, 4);
-    RUN(2, 16, 1, 1024, 8);
-    RUN(2, 16, 1, 2048, 4);
-    RUN(2, 16, 1, 512, 4);
-    RUN(2, 12, 1, 1024, 4);
-    RUN(2, 12, 1, 1024, 8);
-    RUN(2, 20, 1, 1024, 4);
-    RUN(2, 24, 1, 1024, 4);
-    RUN(1, 32, 1, 1024, 4);
-    RUN(1, 32, 1, 1024, 8);
-    RUN(1, 16, 2, 1024, 8);
-    RUN(3, 12, 1, 1024, 4);
-    RUN(3, 10, 1, 1024, 4);
-    RUN(4, 8, 1, 1024, 4);
+#define RUN(P, W, B, T, U, F) run<P, W, B, T, U, F>("<" #P "," #W "," #B "," #T ",u" #U ",f" #F ">", d, n_j, acc, sms)
+    RUN(2, 16, 1, 1024, 4, 1024);
+    RUN(2, 16, 1, 1024, 4, 128);
+    RUN(2, 16, 1, 1024, 4, 64);
+    RUN(2, 16, 1, 1024, 4, 32);
+    RUN(2, 16, 1, 1024, 8, 32);
+    RUN(2, 16, 1, 1024, 4, 16);
+    RUN(2, 16, 1, 1024, 8, 16);
+    RUN(2, 16, 1, 1024, 8, 8);
+    RUN(2, 8, 2, 1024, 4, 32);
+    RUN(1, 4, 4, 512, 8, 32);
+    RUN(1, 4, 4, 512, 8, 16);
+    RUN(1, 4, 4, 512, 4, 1024);
     return 0;
 }
