@@ -339,7 +339,7 @@ def main():
         if res["kernel_ms"]:
             k_ms = statistics.mean(res["kernel_ms"])
             achieved = FLOPS_PER_INTERACTION * res["interactions_per_kernel"] / (k_ms * 1e-3) / 1e12
-            kernel = "force_kernel<2,16,1,1024> (1 launch per step)"
+            kernel = "force_kernel<2,16,1,1024,unroll 32,fold 32> (1 launch per step)"
         else:  # sharded: several force launches per step; report the whole-step rate per GPU
             k_ms = res["total_ms"] / args.steps
             achieved = FLOPS_PER_INTERACTION * n * n / world / (k_ms * 1e-3) / 1e12

@@ -55,7 +55,7 @@ uint64_t nbody_launch_count(void);
 size_t nbody_workspace_bytes(int n_local, int n_total);
 
 /* The launch plan the force kernel will use for `n_local` i-bodies against a j range of `j_len` bodies: kernel shape
- * (1 = 512 threads x 4 i-bodies, 0 = 128 threads x 2 i-bodies), number of i-tiles and of j-splits. A pure function of
+ * (1 = 512 threads x 4 i-bodies, 0 = 256 threads x 2 i-bodies), number of i-tiles and of j-splits. A pure function of
  * its arguments (planned for the 148 SMs of a B200); exposed for tests and for sizing expectations. */
 int nbody_plan_f32(int n_local, int j_len, int* shape_large, int* i_tiles, int* splits);
 

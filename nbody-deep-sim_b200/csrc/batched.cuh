@@ -83,7 +83,7 @@ __device__ __forceinline__ void batched_force(const float4* __restrict__ bodies,
 #pragma unroll
         for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
         if (jb + kBatchedFold <= n) {
-#pragma unroll 8
+#pragma unroll
             for (int u = 0; u < kBatchedFold; ++u) interact(jb + u);
         } else {
             for (int j = jb; j < n; ++j) interact(j);

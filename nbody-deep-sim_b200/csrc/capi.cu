@@ -83,16 +83,17 @@ int current_device_info(const DeviceInfo** out) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Kernel shapes (picked on the GPU with tools/tune_force.cu, profiles/r1_tune_force_variants*.log).
-// LARGE: 512 threads x 4 i-bodies, 1 CTA/SM, 1024-body j tiles, unroll 8 (68.8% of the FP32 roofline in isolation,
-// with the 32-term accumulation runs that cost ~3%). SMALL: 128 threads x 2 i-bodies, 4 CTAs/SM, 512-body j tiles,
-// unroll 8 (65.1%): more, smaller CTAs so that mid-size N still fills 148 SMs.
+// Kernel shapes (picked on the GPU with tools/tune_force.cu, profiles/r1_tune_force_variants*.log). Both run the j loop
+// in fully unrolled 32-body accumulation runs (unroll = kFold = 32).
+// LARGE: 512 threads x 4 i-bodies, 1 CTA/SM, 1024-body j tiles (70.2% of the FP32 roofline in isolation).
+// SMALL: 256 threads x 2 i-bodies, 2 CTAs/SM, 512-body j tiles (67.0%): four times as many CTAs per body, so that
+// mid-size N still fills 148 SMs.
 struct Shape {
     int pairs, warps, min_blocks, tile_j, unroll;
     int tile_i() const { return warps * 32 * pairs * 2; }
 };
-constexpr Shape kLarge{2, 16, 1, 1024, 8};
-constexpr Shape kSmall{1, 4, 4, 512, 8};
+constexpr Shape kLarge{2, 16, 1, 1024, 32};
+constexpr Shape kSmall{1, 8, 2, 512, 32};
 constexpr int kMaxSplits = 16;
 constexpr int kPlanSms = 148;  // B200. Plans (and so workspace sizes) are a pure function of the problem size.
 

@@ -54,8 +54,8 @@ def test_launch_plan_fills_the_machine():
     for n, j in ((1 << 20, 1 << 20), (262144, 262144), (131072, 349525), (65536, 65536), (16384, 16384), (1000, 1000)):
         large, tiles, splits = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         assert lib.nbody_plan_f32(n, j, ctypes.byref(large), ctypes.byref(tiles), ctypes.byref(splits)) == 0
-        tile_i = 2048 if large.value else 256
-        slots = 148 * (1 if large.value else 4)
+        tile_i = 2048 if large.value else 512
+        slots = 148 * (1 if large.value else 2)
         assert tiles.value == -(-n // tile_i) and 1 <= splits.value <= 16
         ctas = tiles.value * splits.value
         if n >= 16384:

@@ -70,17 +70,16 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&acc, sizeof(float) * 3 * n_j));
     CK(cudaMemcpy(d, h.data(), sizeof(float4) * n_j, cudaMemcpyHostToDevice));
 #define RUN(P, W, B, T, U, F) run<P, W, B, T, U, F>("<" #P "," #W "," #B "," #T ",u" #U ",f" #F ">", d, n_j, acc, sms)
-    RUN(2, 16, 1, 1024, 4, 1024);
-    RUN(2, 16, 1, 1024, 4, 128);
-    RUN(2, 16, 1, 1024, 4, 64);
-    RUN(2, 16, 1, 1024, 4, 32);
-    RUN(2, 16, 1, 1024, 8, 32);
-    RUN(2, 16, 1, 1024, 4, 16);
-    RUN(2, 16, 1, 1024, 8, 16);
-    RUN(2, 16, 1, 1024, 8, 8);
-    RUN(2, 8, 2, 1024, 4, 32);
+    RUN(2, 16, 1, 1024, 32, 32);
+    RUN(2, 16, 1, 1024, 16, 16);
+    RUN(2, 16, 1, 1024, 24, 24);
+    RUN(2, 16, 1, 1024, 48, 48);
+    RUN(2, 16, 1, 1024, 64, 64);
+    RUN(2, 8, 2, 1024, 32, 32);
+    RUN(1, 4, 4, 512, 32, 32);
+    RUN(1, 4, 4, 512, 16, 32);
     RUN(1, 4, 4, 512, 8, 32);
-    RUN(1, 4, 4, 512, 8, 16);
-    RUN(1, 4, 4, 512, 4, 1024);
+    RUN(1, 8, 2, 512, 32, 32);
+    RUN(2, 4, 4, 512, 32, 32);
     return 0;
 }
