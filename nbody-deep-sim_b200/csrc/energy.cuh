@@ -10,7 +10,7 @@
 // Per interaction: 3 FADD2 + 3 FMUL2/FFMA2 (r^2) + MUFU.SQRT + FADD2 + MUFU.RCP + FFMA2, so this kernel is MUFU-bound
 // (2 MUFU per interaction), and it is kept apart from the force kernel for that reason. Pairs with j <= i are masked by index (the reference masks the diagonal with +inf and
 // keeps triu(1), simulation.py:107-113); distinct coincident bodies contribute m_i m_j / eps exactly as there.
-// Tile sums are FP32, everything across tiles / threads / CTAs is FP64, and every cross-CTA sum is taken in a
+// Sums over runs of 32 bodies are FP32, everything across runs / tiles / threads / CTAs is FP64, and every cross-CTA sum is taken in a
 // fixed order, so the result is deterministic and closer to the exact value than the reference's FP32 reduction.
 #pragma once
 #include "async_copy.cuh"
@@ -19,6 +19,7 @@ namespace nb {
 
 constexpr int kEnergyStages = 4;
 constexpr int kEnergyLookahead = 2;
+constexpr int kEnergyFold = 32;
 
 struct EnergyParams {
     const float4* bodies;  // (x,y,z,m), all n_total bodies
@@ -108,11 +109,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
         const int count = ring.tile_count(t);
         const float4* __restrict__ tj = ring.tile(t);
         float2 acc[kPairs];
-#pragma unroll
-        for (int q = 0; q < kPairs; ++q) acc[q] = make_float2(0.f, 0.f);
         ring.wait(t);
-#pragma unroll 4
-        for (int jj = 0; jj < count; ++jj) {
+        auto interact = [&](int jj) {
             const float4 b = tj[jj];
             const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
             const float2 bm = make_float2(b.w, b.w);
@@ -131,13 +129,24 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
                 if (jg <= gi[2 * q + 1]) inv.y = 0.f;
                 acc[q] = __ffma2_rn(bm, inv, acc[q]);
             }
+        };
+        // FP32 runs of kEnergyFold bodies, folded into the FP64 row sums (same scheme as force.cuh)
+        for (int jb = 0; jb < count; jb += kEnergyFold) {
+#pragma unroll
+            for (int q = 0; q < kPairs; ++q) acc[q] = make_float2(0.f, 0.f);
+            if (jb + kEnergyFold <= count) {
+#pragma unroll 8
+                for (int u = 0; u < kEnergyFold; ++u) interact(jb + u);
+            } else {
+                for (int jj = jb; jj < count; ++jj) interact(jj);
+            }
+#pragma unroll
+            for (int q = 0; q < kPairs; ++q) {
+                phi[2 * q] += double(acc[q].x);
+                phi[2 * q + 1] += double(acc[q].y);
+            }
         }
         ring.release(t);
-#pragma unroll
-        for (int q = 0; q < kPairs; ++q) {
-            phi[2 * q] += double(acc[q].x);
-            phi[2 * q + 1] += double(acc[q].y);
-        }
     }
     double mine = 0.0;
 #pragma unroll
@@ -207,14 +216,19 @@ __global__ void __launch_bounds__(kTrajEnergyThreads) traj_energy_kernel(const T
     double u = 0.0, k = 0.0;
     for (int i = tid; i < p.n; i += kTrajEnergyThreads) {
         const float4 me = bodies[i];
-        float phi = 0.f;
-        for (int j = i + 1; j < p.n; ++j) {
-            const float4 b = bodies[j];
-            const float dx = b.x - me.x, dy = b.y - me.y, dz = b.z - me.z;
-            const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-            phi = __fmaf_rn(b.w, rcp_approx(sqrt_approx(r2) + p.eps), phi);
+        double phi = 0.0;
+        for (int jb = i + 1; jb < p.n; jb += kEnergyFold) {
+            float run = 0.f;
+            const int jend = min(p.n, jb + kEnergyFold);
+            for (int j = jb; j < jend; ++j) {
+                const float4 b = bodies[j];
+                const float dx = b.x - me.x, dy = b.y - me.y, dz = b.z - me.z;
+                const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                run = __fmaf_rn(b.w, rcp_approx(sqrt_approx(r2) + p.eps), run);
+            }
+            phi += double(run);
         }
-        u += double(me.w) * double(phi);
+        u += double(me.w) * phi;
         const float vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
         const float v2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
         k += double(__fmul_rn(__fmul_rn(0.5f, me.w), v2));
