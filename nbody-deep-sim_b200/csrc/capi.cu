@@ -210,6 +210,8 @@ int launch_force_shape(const ForceParams& p, int i_tiles, int splits, bool exact
 }
 
 int launch_force(const Plan& pl, const ForceParams& p, cudaStream_t stream) {
+    if (size_t(pl.i_tiles) * sizeof(unsigned) > kCounterBytes)
+        return fail(NBODY_ERR_UNSUPPORTED, "force: %d i-tiles exceed the %zu-byte counter scratch", pl.i_tiles, kCounterBytes);
     // softening^2 below the smallest normal float is flushed by MUFU.RSQ: take the index-masked variant.
     const bool exact_diag = !(p.eps2 >= 1.17549435e-38f);
     if (pl.large)
