@@ -40,8 +40,8 @@ FLOPS_PER_INTERACTION = 20.0  # BASELINE.json north_star
 S01 = dict(g_const=4.5e-6, softening=0.05, dt=1e-4)  # s01-dataset-generation.py:44-50 defaults
 L2_FLUSH_BYTES = 256 << 20
 # dram__bytes_read.sum + dram__bytes_write.sum of one force_kernel launch at N = 1,048,576, from the round-1
-# `ncu --set full` capture of this command (profiles/r1_ncu_force_kernel_n1m.txt): 31.27 MB + 14.69 MB.
-NCU_TRAFFIC_BYTES_N1M = 45_952_000
+# `ncu --set full` capture of this command (profiles/r1_ncu_force_kernel_n1m.txt): 40.89 MB + 33.46 MB.
+NCU_TRAFFIC_BYTES_N1M = 74_353_408
 
 
 def make_system(n):
