@@ -123,3 +123,16 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "libnbody_b200.so"))
     with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
         _native.lib()
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under nbody-deep-sim_b200/ may import, load or execute it."""
+    import glob
+
+    from conftest import PKG
+
+    for path in glob.glob(os.path.join(PKG, "**", "*"), recursive=True):
+        if os.path.isdir(path) or not path.endswith((".py", ".cu", ".cuh", ".h")):
+            continue
+        text = open(path).read()
+        assert "oracle" not in text.lower(), path
