@@ -25,7 +25,7 @@ from galaxify import batched, galaxies  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--systems", type=int, default=512)
-    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--bodies", dest="n", type=int, default=512)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--record-every", type=int, nargs="+", default=[0, 1, 10])
     ap.add_argument("--total-systems", type=int, default=0, help="under torchrun: systems of the whole job")
