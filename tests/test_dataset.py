@@ -95,6 +95,25 @@ def test_sink_writes_what_dictwriter_would(tmp_path):
             np.testing.assert_array_equal(got[col].to_numpy().astype(np.float32), want[col].to_numpy().astype(np.float32))
 
 
+def test_sink_keeps_row_order_when_rendering_blocks_in_parallel(tmp_path):
+    n, steps = 400, 300  # 120,000 rows: rendered as several blocks on a thread pool
+    rng = np.random.default_rng(1)
+    states = [FakeState(step=s, step_time=1e-5, positions=rng.standard_normal((n, 3)).astype(np.float32),
+                        velocities=np.full((n, 3), s, np.float32), accelerations=np.zeros((n, 3), np.float32),
+                        u_energy=-1.0, k_energy=float(s)) for s in range(steps)]
+    path = tmp_path / "big.csv"
+    with dataset.CsvSink(str(path)) as sink:
+        assert sink.write_scene(3, "disk", np.arange(n, dtype=np.float64), states) == n * steps
+    got = pd.read_csv(path, float_precision="round_trip")
+    assert len(got) == n * steps
+    np.testing.assert_array_equal(got["step"].to_numpy(), np.repeat(np.arange(steps), n))
+    np.testing.assert_array_equal(got["mass"].to_numpy(), np.tile(np.arange(n, dtype=np.float64), steps))
+    np.testing.assert_array_equal(got["vx"].to_numpy(), np.repeat(np.arange(steps), n).astype(np.float64))
+    want_x = np.concatenate([st.positions[:, 0] for st in states])
+    np.testing.assert_array_equal(got["x"].to_numpy().astype(np.float32), want_x)
+    assert open(path, "rb").read().count(b"\r\n") == n * steps + 1
+
+
 def test_sink_without_energies(tmp_path):
     st = FakeState(0, 1e-3, np.zeros((2, 3), np.float32), np.zeros((2, 3), np.float32), np.zeros((2, 3), np.float32))
     path = tmp_path / "e.csv"
