@@ -71,15 +71,14 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(d, h.data(), sizeof(float4) * n_j, cudaMemcpyHostToDevice));
 #define RUN(P, W, B, T, U, F) run<P, W, B, T, U, F>("<" #P "," #W "," #B "," #T ",u" #U ",f" #F ">", d, n_j, acc, sms)
     RUN(2, 16, 1, 1024, 32, 32);
-    RUN(2, 16, 1, 1024, 16, 16);
-    RUN(2, 16, 1, 1024, 24, 24);
-    RUN(2, 16, 1, 1024, 48, 48);
-    RUN(2, 16, 1, 1024, 64, 64);
     RUN(2, 8, 2, 1024, 32, 32);
-    RUN(1, 4, 4, 512, 32, 32);
-    RUN(1, 4, 4, 512, 16, 32);
-    RUN(1, 4, 4, 512, 8, 32);
+    RUN(2, 8, 3, 1024, 32, 32);
+    RUN(2, 24, 1, 1024, 32, 32);
+    RUN(2, 12, 2, 512, 32, 32);
+    RUN(2, 16, 1, 1024, 8, 32);
+    RUN(2, 16, 1, 1024, 4, 32);
     RUN(1, 8, 2, 512, 32, 32);
-    RUN(2, 4, 4, 512, 32, 32);
+    RUN(1, 8, 4, 512, 32, 32);
+    RUN(1, 16, 2, 512, 32, 32);
     return 0;
 }
