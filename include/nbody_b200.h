@@ -94,17 +94,19 @@ int nbody_energies_f32(const float* pos, const float* vel, const float* mass, in
  *
  * nbody_shard_prepare_f32: writes this rank's slice of `bodies` from (pos, mass) and, for leapfrog, performs the
  *   opening half-kick + drift (simulation.py:164-166) into pos / vhalf first. The caller then all-gathers bodies.
- * nbody_shard_force_f32: accumulates the j-range [j_begin, j_end) for the local i-bodies. A step may be split
- *   over several calls (own slice first, remote slices as they arrive); `part` / `n_parts` identify them and the
- *   last call to complete runs the integrator epilogue and writes this rank's slice of `bodies_next`. */
+ * nbody_shard_force_f32: accumulates the j-range [j_begin, j_end), plus an optional second range
+ *   [j2_begin, j2_end) (pass j2_begin >= j2_end for none), for the local i-bodies. A step may be split over several
+ *   calls (own slice first, the rest once gathered); `part` / `n_parts` identify them and the last call to complete
+ *   runs the integrator epilogue and writes this rank's slice of `bodies_next`. Bodies with zero mass contribute
+ *   nothing, so ranges may include padding entries as long as those sit away from every real body. */
 size_t nbody_shard_workspace_bytes(int n_local, int n_total, int n_parts);
 int nbody_shard_prepare_f32(int integrator, float* pos, const float* vel, const float* acc, const float* mass,
                             float* vhalf, float* bodies, int i_begin, int n_local, float dt, float half_dt,
                             void* stream);
 int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_next, int n_total, int i_begin,
-                          int n_local, int j_begin, int j_end, int part, int n_parts, float* pos, float* vel,
-                          float* acc, float* vhalf, float g, float eps2, float dt, float half_dt, int do_next,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          int n_local, int j_begin, int j_end, int j2_begin, int j2_end, int part, int n_parts,
+                          float* pos, float* vel, float* acc, float* vhalf, float g, float eps2, float dt,
+                          float half_dt, int do_next, void* workspace, size_t workspace_bytes, void* stream);
 
 /* This rank's share of compute_energies (simulation.py:91-115): u = -G sum_{i local} m_i sum_{j > i} m_j/(|r_ij|+eps)
  * over the full body array (pad slots must hold zero masses), k over the local velocities. The caller sums the two

@@ -59,26 +59,31 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
 
 // Shared-memory ring of j-body tiles fed by TMA bulk copies.
 //
-// One lane of the CTA is the producer: issue(t) arms full[t % kStages] with the tile's byte count and starts the
-// copy; it first waits on empty[] until every warp has released the stage's previous occupant. Consumers call
-// wait(t) before reading tile t and release(t) (one arrive per warp) when done. Tiles are kTileJ float4 bodies.
+// The j range is one or two contiguous segments of the body array (two when a launch covers "everything but the
+// rank's own slice"); tiles are numbered through both. One lane of the CTA is the producer: issue(t) arms
+// full[t % kStages] with the tile's byte count and starts the copy; it first waits on empty[] until every warp has
+// released the stage's previous occupant. Consumers call wait(t) before reading tile t and release(t) (one arrive
+// per warp) when done. Tiles are kTileJ float4 bodies.
 template <int kTileJ, int kStages, int kWarps>
 struct TileRing {
     float4* tiles;
     uint64_t* full;
     uint64_t* empty;
-    const float4* src;  // first body of the j range
-    int count;          // bodies in the j range
+    const float4* src[2];  // first body of each segment
+    int count[2];          // bodies in each segment
+    int tiles0;            // tiles of segment 0
 
     static constexpr size_t smem_bytes() {
         return size_t(kStages) * kTileJ * sizeof(float4) + 2 * kStages * sizeof(uint64_t);
     }
-    __device__ __forceinline__ void attach(unsigned char* smem, const float4* src_, int count_) {
+    __device__ __forceinline__ void attach(unsigned char* smem, const float4* src0, int count0,
+                                           const float4* src1 = nullptr, int count1 = 0) {
         tiles = reinterpret_cast<float4*>(smem);
         full = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * kTileJ * sizeof(float4));
         empty = full + kStages;
-        src = src_;
-        count = count_;
+        src[0] = src0, src[1] = src1;
+        count[0] = max(count0, 0), count[1] = max(count1, 0);
+        tiles0 = (count[0] + kTileJ - 1) / kTileJ;
     }
     // Call from one thread, then __syncthreads().
     __device__ __forceinline__ void init_barriers() {
@@ -88,15 +93,18 @@ struct TileRing {
         }
         mbar_fence_init();
     }
-    __device__ __forceinline__ int num_tiles() const { return (count + kTileJ - 1) / kTileJ; }
-    __device__ __forceinline__ int tile_count(int t) const { return min(kTileJ, count - t * kTileJ); }
+    __device__ __forceinline__ int num_tiles() const { return tiles0 + (count[1] + kTileJ - 1) / kTileJ; }
+    __device__ __forceinline__ int segment(int t) const { return t < tiles0 ? 0 : 1; }
+    // Offset of tile t's first body within its segment.
+    __device__ __forceinline__ int tile_offset(int t) const { return (t < tiles0 ? t : t - tiles0) * kTileJ; }
+    __device__ __forceinline__ int tile_count(int t) const { return min(kTileJ, count[segment(t)] - tile_offset(t)); }
     __device__ __forceinline__ const float4* tile(int t) const { return tiles + size_t(t % kStages) * kTileJ; }
     __device__ __forceinline__ void issue(int t) {
         const int s = t % kStages;
         if (t >= kStages) mbar_wait(&empty[s], ((t / kStages) & 1) ^ 1);
         const uint32_t bytes = uint32_t(tile_count(t)) * sizeof(float4);
         mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_copy_g2s(tiles + size_t(s) * kTileJ, src + size_t(t) * kTileJ, bytes, &full[s]);
+        bulk_copy_g2s(tiles + size_t(s) * kTileJ, src[segment(t)] + tile_offset(t), bytes, &full[s]);
     }
     __device__ __forceinline__ void wait(int t) { mbar_wait(&full[t % kStages], (t / kStages) & 1); }
     // All lanes of a warp call this after their last read of tile t.

@@ -466,9 +466,9 @@ int nbody_shard_prepare_f32(int integrator, float* pos, const float* vel, const 
 }
 
 int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_next, int n_total, int i_begin,
-                          int n_local, int j_begin, int j_end, int part, int n_parts, float* pos, float* vel,
-                          float* acc, float* vhalf, float g, float eps2, float dt, float half_dt, int do_next,
-                          void* workspace, size_t workspace_bytes, void* stream_) {
+                          int n_local, int j_begin, int j_end, int j2_begin, int j2_end, int part, int n_parts,
+                          float* pos, float* vel, float* acc, float* vhalf, float g, float eps2, float dt,
+                          float half_dt, int do_next, void* workspace, size_t workspace_bytes, void* stream_) {
     int mode = MODE_ACCEL;
     if (integrator != 0)
         if (int st = mode_of(integrator, &mode)) return st;
@@ -476,10 +476,12 @@ int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_nex
     if (mode != MODE_ACCEL && (!pos || !vel || !bodies_next))
         return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_force: integrator needs pos, vel, bodies_next");
     if (mode == MODE_LEAPFROG && !vhalf) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_force: leapfrog needs vhalf");
+    const bool second = j2_begin < j2_end;
     if (n_local < 1 || i_begin < 0 || i_begin + n_local > n_total || j_begin < 0 || j_end > n_total ||
-        j_begin >= j_end || part < 0 || part >= n_parts)
-        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_force: bad range (i %d+%d, j [%d,%d), part %d/%d, n %d)", i_begin,
-                    n_local, j_begin, j_end, part, n_parts, n_total);
+        j_begin > j_end || (second && (j2_begin < 0 || j2_end > n_total)) || (j_begin == j_end && !second) ||
+        part < 0 || part >= n_parts)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_force: bad range (i %d+%d, j [%d,%d) + [%d,%d), part %d/%d, n %d)",
+                    i_begin, n_local, j_begin, j_end, j2_begin, j2_end, part, n_parts, n_total);
     const DeviceInfo* dev;
     if (int st = current_device_info(&dev)) return st;
     Workspace w = carve(workspace, n_local, n_total, n_parts, false);
@@ -493,6 +495,7 @@ int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_nex
     ForceParams fp{};
     fp.bodies = reinterpret_cast<const float4*>(bodies), fp.bodies_next = reinterpret_cast<float4*>(bodies_next);
     fp.j_begin = j_begin, fp.j_end = j_end, fp.i_begin = i_begin, fp.i_count = n_local;
+    fp.j2_begin = second ? j2_begin : 0, fp.j2_end = second ? j2_end : 0;
     fp.eps2 = eps2, fp.g = g;
     fp.partial = w.partial, fp.partial_stride = w.partial_stride;
     fp.split_offset = part * pl.splits, fp.splits_total = n_parts * pl.splits, fp.counters = w.counters;

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
 
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + kEnergyLookahead < ntiles) ring.issue(t + kEnergyLookahead);
-        const int jt = j_lo + t * kTileJ;
+        const int jt = j_lo + ring.tile_offset(t);
         const int count = ring.tile_count(t);
         const float4* __restrict__ tj = ring.tile(t);
         float2 acc[kPairs];

@@ -36,7 +36,8 @@ enum Mode : int { MODE_ACCEL = 0, MODE_LEAPFROG = 1, MODE_EULER = 2 };
 struct ForceParams {
     const float4* bodies;  // current (x,y,z,m) of ALL bodies: j source, and i source at [i_begin, i_begin+i_count)
     float4* bodies_next;   // where drifted bodies are written (global index), may be null
-    int j_begin, j_end;    // j range this launch covers
+    int j_begin, j_end;    // j range this launch covers ...
+    int j2_begin, j2_end;  // ... plus an optional second range (empty when j2_begin >= j2_end)
     int i_begin, i_count;  // i range this launch covers (global index of first, count)
     float eps2, g;
     // split-j reduction scratch
@@ -117,14 +118,19 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const Fo
 
     const int tid = threadIdx.x;
 
-    // j range of this split (contiguous, balanced to whole bodies)
-    const int nj = p.j_end - p.j_begin;
-    const int per = (nj + gridDim.y - 1) / gridDim.y;
-    const int j0 = p.j_begin + min(int(blockIdx.y) * per, nj);
-    const int j1 = p.j_begin + min(int(blockIdx.y + 1) * per, nj);
+    // j ranges of this split: an even share of each of the launch's (one or two) ranges
+    auto share = [&](int begin, int end, int& lo, int& hi) {
+        const int len = max(end - begin, 0);
+        const int per = (len + gridDim.y - 1) / gridDim.y;
+        lo = begin + min(int(blockIdx.y) * per, len);
+        hi = begin + min(int(blockIdx.y + 1) * per, len);
+    };
+    int j0, j1, k0, k1;
+    share(p.j_begin, p.j_end, j0, j1);
+    share(p.j2_begin, p.j2_end, k0, k1);
 
     Ring ring;
-    ring.attach(smem_raw, p.bodies + j0, j1 - j0);
+    ring.attach(smem_raw, p.bodies + j0, j1 - j0, p.bodies + k0, k1 - k0);
     const int ntiles = ring.num_tiles();
     if (tid == 0) ring.init_barriers();
     __syncthreads();
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) force_kernel(const Fo
 
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + kLookahead < ntiles) ring.issue(t + kLookahead);
-        const int jt = j0 + t * kTileJ;
+        const int jt = (ring.segment(t) == 0 ? j0 : k0) + ring.tile_offset(t);  // global index of the tile's first body
         const int count = ring.tile_count(t);
         const float4* __restrict__ tj = ring.tile(t);
         ring.wait(t);

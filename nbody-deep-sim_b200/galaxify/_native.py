@@ -57,8 +57,8 @@ SIGNATURES = {
     ),
     "nbody_shard_force_f32": (
         c_int,
-        [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-         c_void_p, c_float, c_float, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p],
+        [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p],
     ),
     "nbody_shard_energies_f32": (
         c_int,

@@ -5,13 +5,16 @@ keeps the reference's keyword arguments (calc_energy defaults to False here); ev
 arrays and keeps only its slice. Energies are reduced over ranks with one all-reduce of two doubles.
 
 Layout: the body array (x,y,z,m float4) has world_size slots of `n_pad = ceil(n / world_size)` bodies; rank r owns
-global indices [r*n_pad, r*n_pad + count_r). Padding bodies are never read: each step is a set of j-range "parts",
-one per rank slice (adjacent slices merge when there is no padding), and parts only cover real bodies.
+global indices [r*n_pad, r*n_pad + count_r). Padding entries are massless and parked far away (1e18), so kernels may
+sweep whole slots: they contribute exactly zero.
 
-One step on a rank (leapfrog; Euler differs only in the epilogue):
-    all_gather(bodies_cur)  [NCCL stream]   ||   force(part = own slice)  [compute stream]
-    wait for the gather, force(remaining parts); the last part to finish runs the fused kick/kick/drift epilogue
-    and writes the rank's slice of bodies_next, which the next step gathers.
+One step on a rank (leapfrog; Euler differs only in the epilogue), with `overlap` (default for n >= 524,288):
+    all_gather(bodies_cur)  [NCCL stream]   ||   force(part 0 = own slice)  [compute stream]
+    wait for the gather, force(part 1 = everything before and after the own slot, one launch over two ranges);
+    the last part to finish runs the fused kick/kick/drift epilogue and writes the rank's slice of bodies_next,
+    which the next step gathers.
+Without overlap (smaller systems, where one more launch per step costs more than the gather it hides): wait for the
+gather, then a single launch over the whole array.
 The force accumulates into the same split-j scratch as the single-GPU path, so a rank computes exactly what the
 single-GPU kernel computes for its i-bodies up to FP32 summation order (the j splits differ).
 """
@@ -35,26 +38,25 @@ def shard_layout(n: int, world_size: int):
     return n_pad, counts
 
 
-def step_parts(rank: int, n_pad: int, counts):
-    """j ranges (global slot indices) of one step for `rank`: own slice first, then the other ranks' slices with
-    adjacent ones merged (slices are adjacent exactly when the earlier slot has no padding)."""
-    parts = [(rank * n_pad, rank * n_pad + counts[rank])]
-    for r, c in enumerate(counts):
-        if r == rank or c == 0:
-            continue
-        lo, hi = r * n_pad, r * n_pad + c
-        if len(parts) > 1 and parts[-1][1] == lo:
-            parts[-1] = (parts[-1][0], hi)
-        else:
-            parts.append((lo, hi))
-    return parts
+def step_parts(rank: int, n_pad: int, counts, overlap: bool):
+    """j ranges of one step for `rank`, each part a pair of half-open slot ranges ((lo, hi), (lo2, hi2)).
+
+    With overlap, part 0 is the rank's own slice (computed while the all-gather is in flight) and part 1 everything
+    before and after the rank's slot; without, a single part sweeps the whole array once the gather is done.
+    Ranges run over whole slots, padding entries included: those are massless and parked far away, so they add
+    exactly zero."""
+    total = len(counts) * n_pad
+    lo, hi = rank * n_pad, rank * n_pad + counts[rank]
+    if not overlap or len(counts) == 1:
+        return [((0, total), (0, 0))]
+    return [((lo, hi), (0, 0)), ((0, lo), (lo + n_pad, total))]
 
 
 class ShardedSimulator:
     _integrator = None
 
     def __init__(self, *, positions, velocities, masses, g_const: float = 1.0, softening: float = 0.1,
-                 dt: float = 0.01, calc_energy: bool = False, device: str = None, group=None):
+                 dt: float = 0.01, calc_energy: bool = False, device: str = None, group=None, overlap: bool = None):
         if device is not None and device not in ["cuda", "cpu"]:
             raise ValueError("device debe ser 'cuda', 'cpu' o None")
         self.group = group
@@ -85,7 +87,10 @@ class ShardedSimulator:
         self._bodies = [torch.zeros((self.world_size * self.n_pad, 4), dtype=torch.float32, device=dev) for _ in range(2)]
         for b in self._bodies:  # pad entries of the own slot: massless and far away, so that no kernel that sweeps the
             b[self.i_begin + self.n_local : self.i_begin + self.n_pad, :3] = 1e18  # whole array can divide by zero
-        self._parts = step_parts(self.rank, self.n_pad, self.counts)
+        # Overlapping the gather with the own-slice force costs one more launch per step: worth it only when a step
+        # is long compared to a launch (the gather itself is tens of microseconds either way).
+        self.overlap = (self.n >= 524288) if overlap is None else bool(overlap)
+        self._parts = step_parts(self.rank, self.n_pad, self.counts, self.overlap)
         self._workspace = self._alloc_workspace()
         self.launches_per_step = len(self._parts)
         # initial accelerations (simulation.py:69)
@@ -121,11 +126,12 @@ class ShardedSimulator:
                      _ptr(self.accelerations), _ptr(self.masses), _ptr(self._vhalf), _ptr(bodies), self.i_begin,
                      self.n_local, s["dt"], s["half_dt"], self._stream())
 
-    def _force(self, integrator, bodies, bodies_next, part, j_range, do_next):
+    def _force(self, integrator, bodies, bodies_next, part, j_ranges, do_next):
         s = self._scalars()
         ws = self._workspace
+        (j0, j1), (k0, k1) = j_ranges
         _native.call("nbody_shard_force_f32", integrator, _ptr(bodies), _ptr(bodies_next),
-                     self.world_size * self.n_pad, self.i_begin, self.n_local, j_range[0], j_range[1], part,
+                     self.world_size * self.n_pad, self.i_begin, self.n_local, j0, j1, k0, k1, part,
                      len(self._parts), _ptr(self.positions), _ptr(self.velocities), _ptr(self.accelerations),
                      _ptr(self._vhalf), s["g"], s["eps2"], s["dt"], s["half_dt"], do_next, _ptr(ws), ws.numel(),
                      self._stream())
@@ -160,7 +166,13 @@ class ShardedSimulator:
     # ------------------------------------------------------------------ stepping
 
     def _force_all(self, integrator, bodies, bodies_next, do_next, gather_work=None):
-        """Own part first (overlaps the gather), then the remote parts; the last launch runs the epilogue."""
+        """With overlap: own part while the gather is in flight, then the rest. Without: wait, then one sweep.
+        The last launch runs the epilogue."""
+        if len(self._parts) == 1:
+            if gather_work is not None:
+                gather_work.wait()
+            self._force(integrator, bodies, bodies_next, 0, self._parts[0], do_next)
+            return
         self._force(integrator, bodies, bodies_next, 0, self._parts[0], do_next)
         if gather_work is not None:
             gather_work.wait()

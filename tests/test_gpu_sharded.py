@@ -23,7 +23,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n, integrator, steps, out_dir):
+def _worker(rank, world, port, n, integrator, steps, out_dir, overlap):
     import sys
 
     for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
@@ -38,7 +38,8 @@ def _worker(rank, world, port, n, integrator, steps, out_dir):
         pos, vel, mass = galaxies.generate_disk(n_bodies=n, total_mass=1.0, radial_scale=3.0, height_scale=0.3,
                                                 g_const=4.5e-6, black_hole_mass=0.01, seed=n)
         cls = sharded.ShardedLeapFrogSimulator if integrator == "leapfrog" else sharded.ShardedEulerSimulator
-        sim = cls(positions=pos, velocities=vel, masses=mass, g_const=4.5e-6, softening=0.05, dt=1e-4, calc_energy=True)
+        sim = cls(positions=pos, velocities=vel, masses=mass, g_const=4.5e-6, softening=0.05, dt=1e-4, calc_energy=True,
+                  overlap=overlap)
         acc0 = sim.gather_state()[2].numpy()
         e0 = sim.compute_energies()
         states = sim.run(steps)
@@ -51,10 +52,10 @@ def _worker(rank, world, port, n, integrator, steps, out_dir):
         dist.destroy_process_group()
 
 
-def _check(tmp_path, world, n, integrator, steps):
+def _check(tmp_path, world, n, integrator, steps, overlap=None):
     from galaxify import galaxies, simulation
 
-    mp.spawn(_worker, args=(world, _free_port(), n, integrator, steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, integrator, steps, str(tmp_path), overlap), nprocs=world, join=True)
     z = np.load(os.path.join(str(tmp_path), "out.npz"))
     pos, vel, mass = galaxies.generate_disk(n_bodies=n, total_mass=1.0, radial_scale=3.0, height_scale=0.3,
                                             g_const=4.5e-6, black_hole_mass=0.01, seed=n)
@@ -83,6 +84,8 @@ def test_sharded_world1_equals_single_gpu(tmp_path, n, integrator):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("integrator,n", [("leapfrog", 20001), ("euler", 4096), ("leapfrog", 262144)])
-def test_sharded_world2_equals_single_gpu(tmp_path, integrator, n):
-    _check(tmp_path, 2, n, integrator, 3)
+@pytest.mark.parametrize("integrator,n,overlap", [("leapfrog", 20001, True), ("leapfrog", 20001, False),
+                                                  ("euler", 4097, True), ("euler", 4096, False),
+                                                  ("leapfrog", 262144, True), ("leapfrog", 262144, None)])
+def test_sharded_world2_equals_single_gpu(tmp_path, integrator, n, overlap):
+    _check(tmp_path, 2, n, integrator, 3, overlap)

@@ -49,19 +49,31 @@ def _emulated_class(base):
             bodies[sl, :3] = torch.from_numpy(pos)
             bodies[sl, 3] = self.masses
 
-        def _force(self, integrator, bodies, bodies_next, part, j_range, do_next):
+        def _force(self, integrator, bodies, bodies_next, part, j_ranges, do_next):
             ws = self._workspace
             if part == 0:
                 ws["sum"], ws["seen"] = np.zeros((self.n_local, 3)), 0
             b = bodies.numpy()
-            lo, hi = j_range
-            mine = b[self.i_begin : self.i_begin + self.n_local]
-            # un-scaled partial sum of this j range for the local bodies, FP64 (the kernel: FP32 tiles + Kahan)
-            both = np.concatenate([mine, b[lo:hi]])
-            full = oracle.accelerations_f64(both[:, :3], both[:, 3], 1.0, self.softening, rows=slice(0, self.n_local))
+            own_lo, own_hi = self.i_begin, self.i_begin + self.n_local
+            mine = b[own_lo:own_hi]
             own = oracle.accelerations_f64(mine[:, :3], mine[:, 3], 1.0, self.softening)
-            overlap = self.i_begin >= lo and self.i_begin < hi  # the part IS the own slice
-            ws["sum"] += own if overlap else full - own
+
+            def others(lo, hi):  # un-scaled sum over the j slots [lo, hi), none of them the rank's own bodies
+                if hi <= lo:
+                    return 0.0
+                both = np.concatenate([mine, b[lo:hi]])
+                full = oracle.accelerations_f64(both[:, :3], both[:, 3], 1.0, self.softening, rows=slice(0, self.n_local))
+                return full - own
+
+            # FP64 partial sum of this part's ranges (the kernel: FP32 runs folded into FP64)
+            for lo, hi in j_ranges:
+                if hi <= lo:
+                    continue
+                if lo <= own_lo and own_hi <= hi:  # the range contains the own slice: split around it
+                    ws["sum"] += others(lo, own_lo) + own + others(own_hi, hi)
+                else:
+                    assert hi <= own_lo or lo >= own_hi, "ranges may not cut through the own slice"
+                    ws["sum"] += others(lo, hi)
             ws["seen"] += 1
             if ws["seen"] < len(self._parts):
                 return
@@ -89,7 +101,7 @@ def _emulated_class(base):
     return Emulated
 
 
-def _worker(rank, world, port, case, integrator, steps, out_dir):
+def _worker(rank, world, port, case, integrator, steps, out_dir, overlap):
     import sys
 
     for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
@@ -102,7 +114,8 @@ def _worker(rank, world, port, case, integrator, steps, out_dir):
 
         g = load_golden(case)
         base = sharded.ShardedLeapFrogSimulator if integrator == "leapfrog" else sharded.ShardedEulerSimulator
-        sim = _emulated_class(base)(positions=g["ic_pos"], velocities=g["ic_vel"], masses=g["ic_mass"], **g.sim)
+        sim = _emulated_class(base)(positions=g["ic_pos"], velocities=g["ic_vel"], masses=g["ic_mass"], overlap=overlap,
+                                    **g.sim)
         acc0 = sim.gather_state()[2].numpy()
         states = sim.run(steps)
         pos, vel, acc = (t.numpy() for t in sim.gather_state())
@@ -113,14 +126,15 @@ def _worker(rank, world, port, case, integrator, steps, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,case,integrator", [(2, "spiral_n25_leapfrog", "leapfrog"),
-                                                   (2, "disk_n500_euler", "euler"),
-                                                   (3, "disk_n500_leapfrog", "leapfrog")])
-def test_sharded_protocol_matches_single_process_oracle(tmp_path, world, case, integrator):
+@pytest.mark.parametrize("world,case,integrator,overlap", [(2, "spiral_n25_leapfrog", "leapfrog", True),
+                                                           (2, "disk_n500_euler", "euler", False),
+                                                           (3, "disk_n500_leapfrog", "leapfrog", True),
+                                                           (3, "spiral_n500_euler", "euler", None)])
+def test_sharded_protocol_matches_single_process_oracle(tmp_path, world, case, integrator, overlap):
     from oracle import galaxify_oracle as oracle
 
     steps = 5
-    mp.spawn(_worker, args=(world, _free_port(), case, integrator, steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), case, integrator, steps, str(tmp_path), overlap), nprocs=world, join=True)
     g = load_golden(case)
     ref, st = oracle.run(g["ic_pos"], g["ic_vel"], g["ic_mass"], integrator=integrator, steps=steps, **g.sim)
     acc0 = oracle.accelerations(g["ic_pos"], g["ic_mass"], g.sim["g_const"], g.sim["softening"]).numpy()
@@ -141,18 +155,21 @@ def test_sharded_protocol_matches_single_process_oracle(tmp_path, world, case, i
 def test_layout_and_parts_cover_every_body_exactly_once():
     from galaxify.sharded import shard_layout, step_parts
 
-    for n, world in ((16, 4), (17, 4), (1 << 20, 8), (5, 2), (1000, 3), (262144, 8)):
+    for n, world in ((16, 4), (17, 4), (1 << 20, 8), (5, 2), (1000, 3), (262144, 8), (7, 1)):
         n_pad, counts = shard_layout(n, world)
         assert sum(counts) == n and max(counts) == n_pad
         for rank in range(world):
-            parts = step_parts(rank, n_pad, counts)
-            assert parts[0] == (rank * n_pad, rank * n_pad + counts[rank])
-            covered = np.zeros(world * n_pad, dtype=int)
-            for lo, hi in parts:
-                covered[lo:hi] += 1
-            real = np.zeros(world * n_pad, dtype=int)
-            for r, c in enumerate(counts):
-                real[r * n_pad : r * n_pad + c] = 1
-            np.testing.assert_array_equal(covered, real)
-            if n % world == 0:
-                assert len(parts) <= 3
+            for overlap in (True, False):
+                parts = step_parts(rank, n_pad, counts, overlap)
+                assert len(parts) == (2 if overlap and world > 1 else 1)
+                covered = np.zeros(world * n_pad, dtype=int)
+                for ranges in parts:
+                    for lo, hi in ranges:
+                        covered[lo:hi] += 1
+                real = np.zeros(world * n_pad, dtype=bool)
+                for r, c in enumerate(counts):
+                    real[r * n_pad : r * n_pad + c] = True
+                np.testing.assert_array_equal(covered[real], 1)  # every body exactly once
+                assert covered[~real].max(initial=0) <= 1  # padding entries (massless, far away) at most once
+                if overlap and world > 1:
+                    assert parts[0] == ((rank * n_pad, rank * n_pad + counts[rank]), (0, 0))
