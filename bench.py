@@ -69,8 +69,9 @@ class ClockSampler:
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.1):
         self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.period = float(os.environ.get("NBODY_BENCH_CLOCK_PERIOD", period))
         try:
             import pynvml
 
@@ -94,7 +95,7 @@ class ClockSampler:
                 self.reasons.update(name for bit, name in self.REASONS.items() if mask & bit and bit != 0x1)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         if self.nv:
