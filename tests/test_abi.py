@@ -136,3 +136,29 @@ def test_product_package_never_imports_the_oracle():
             continue
         text = open(path).read()
         assert "oracle" not in text.lower(), path
+
+
+def test_binding_argument_counts_match_the_header():
+    """Every ctypes signature has as many arguments as the C declaration (a mismatch corrupts the stack silently)."""
+    text = open(os.path.join(ROOT, "include", "nbody_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = dict(re.findall(r"\b(nbody_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(decls) == set(_native.SIGNATURES)
+    for name, params in decls.items():
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_native.SIGNATURES[name][1]), (name, n, len(_native.SIGNATURES[name][1]))
+    # and every slot has the right kind: pointer, float, size_t or int
+    for name, params in decls.items():
+        params = " ".join(params.split())
+        if params in ("", "void"):
+            continue
+        for ctype, decl in zip(_native.SIGNATURES[name][1], params.split(",")):
+            if "*" in decl:
+                assert ctype is ctypes.c_void_p or issubclass(ctype, ctypes._Pointer), (name, decl)
+            elif "float" in decl:
+                assert ctype is ctypes.c_float, (name, decl)
+            elif "size_t" in decl:
+                assert ctype is ctypes.c_size_t, (name, decl)
+            else:
+                assert ctype is ctypes.c_int, (name, decl)
