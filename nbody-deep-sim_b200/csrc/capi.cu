@@ -624,7 +624,7 @@ struct HostCache {
     size_t bytes = 0;
 };
 HostCache g_host[kMaxDevices];
-std::mutex g_host_mutex;
+std::mutex g_host_mutex[kMaxDevices];  // one per device: threads driving different GPUs do not serialise
 
 int host_scratch(int device, size_t bytes, HostCache** out) {
     if (device < 0 || device >= kMaxDevices) return fail(NBODY_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", device);
@@ -646,7 +646,8 @@ int nbody_accel_host_f32(const float* pos, const float* mass, float* acc, int n,
                          uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
     if (!pos || !mass || !acc) return fail(NBODY_ERR_INVALID_ARGUMENT, "accel_host: null pointer");
     if (n < 1) return fail(NBODY_ERR_INVALID_ARGUMENT, "accel_host: n = %d", n);
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    if (device < 0 || device >= kMaxDevices) return fail(NBODY_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_host_mutex[device]);
     const size_t b3 = align_up(size_t(n) * 12, 256), b1 = align_up(size_t(n) * 4, 256);
     const size_t ws = nbody_workspace_bytes(n, n);
     HostCache* c;
@@ -674,7 +675,8 @@ int nbody_integrate_host_f32(int integrator, float* pos, float* vel, float* acc,
     if (n < 1 || steps < 0) return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate_host: n = %d, steps = %d", n, steps);
     if ((traj || energies) && record_every < 1)
         return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate_host: record_every = %d", record_every);
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    if (device < 0 || device >= kMaxDevices) return fail(NBODY_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_host_mutex[device]);
     const size_t slots = (traj || energies) ? size_t(steps / record_every) : 0;
     const size_t b3 = align_up(size_t(n) * 12, 256), b1 = align_up(size_t(n) * 4, 256);
     const size_t b_traj = traj ? align_up(slots * 3 * size_t(n) * 12, 256) : 0;
@@ -711,8 +713,8 @@ int nbody_integrate_host_f32(int integrator, float* pos, float* vel, float* acc,
 }
 
 int nbody_host_cache_release(void) {
-    std::lock_guard<std::mutex> lock(g_host_mutex);
     for (int d = 0; d < kMaxDevices; ++d) {
+        std::lock_guard<std::mutex> lock(g_host_mutex[d]);
         HostCache& c = g_host[d];
         if (!c.buf && !c.stream) continue;
         NB_CUDA(cudaSetDevice(d));
