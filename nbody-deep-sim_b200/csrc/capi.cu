@@ -148,7 +148,6 @@ struct Workspace {
     double* partial;
     unsigned* counters;
     double* energy_partial;
-    double* energy_out;  // 2 doubles, scratch target when the caller wants no energies
     int partial_stride;
     size_t total;
 };
@@ -175,7 +174,6 @@ Workspace carve(void* base, int n_local, int n_total, int n_parts, bool own_bodi
     w.partial = static_cast<double*>(take(size_t(slots) * 3 * w.partial_stride * sizeof(double)));
     w.counters = static_cast<unsigned*>(take(kCounterBytes));
     w.energy_partial = static_cast<double*>(take(kEnergyPartialBytes));
-    w.energy_out = static_cast<double*>(take(256));
     w.total = off;
     return w;
 }
