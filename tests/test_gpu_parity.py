@@ -179,3 +179,29 @@ def test_ill_conditioned_bodies_near_the_centre():
     err = rel_rows(acc[rows], want)
     assert kappa.max() > 100  # the sample does contain ill-conditioned bodies
     assert np.all(err <= np.maximum(ACC_RTOL, 1e-7 * kappa)), (err.max(), (err / kappa).max())
+
+
+@pytest.mark.parametrize("integrator", ["leapfrog", "euler"])
+@pytest.mark.parametrize("kind,n", [("disk", 3000), ("spiral", 2500)])
+def test_mid_size_trajectory_and_energies_vs_cpu_oracle(integrator, kind, n):
+    """Sizes just above the persistent-kernel limit, so the tiled kernel with its fused epilogue (split-j, both
+    integrators) is compared step by step with the CPU restatement of the reference, energies included."""
+    from galaxify import galaxies, simulation
+    from oracle import galaxify_oracle as oracle
+
+    gen = galaxies.generate_disk if kind == "disk" else galaxies.generate_spiral
+    pos, vel, mass = gen(n_bodies=n, total_mass=1.0, radial_scale=3.0, height_scale=0.3, g_const=4.5e-6,
+                         black_hole_mass=0.01, seed=17)
+    kw = dict(g_const=4.5e-6, softening=0.05, dt=1e-4)
+    cls = simulation.LeapFrogSimulator if integrator == "leapfrog" else simulation.EulerSimulator
+    sim = cls(positions=pos, velocities=vel, masses=mass, calc_energy=True, **kw)
+    steps = 6
+    states = sim.run(steps)
+    ref, _ = oracle.run(pos, vel, mass, integrator=integrator, steps=steps, calc_energy=True, **kw)
+    for s in range(steps):
+        st, want = states[s], ref[s]
+        assert np.abs(st.positions.numpy() - want["pos"]).max() <= TRAJ_RTOL * np.abs(want["pos"]).max(), s
+        assert np.abs(st.velocities.numpy() - want["vel"]).max() <= TRAJ_RTOL * np.abs(want["vel"]).max(), s
+        assert rel_rows(st.accelerations.numpy(), want["acc"]).max() <= ACC_RTOL, s
+        assert abs(st.u_energy - want["u"]) <= ENERGY_RTOL * abs(want["u"]), s
+        assert abs(st.k_energy - want["k"]) <= ENERGY_RTOL * abs(want["k"]), s
