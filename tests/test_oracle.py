@@ -81,3 +81,36 @@ def test_c_oracle_row_range():
     full = c_oracle.accelerations_f64(g["ic_pos"], g["ic_mass"], 4.5e-6, 0.05)
     part = c_oracle.accelerations_f64(g["ic_pos"], g["ic_mass"], 4.5e-6, 0.05, 100, 217)
     np.testing.assert_array_equal(part, full[100:217])
+
+
+def _random_system(seed, n):
+    rng = np.random.default_rng(seed)
+    pos = rng.standard_normal((n, 3)) * rng.choice([0.1, 1.0, 10.0])
+    vel = rng.standard_normal((n, 3)) * 1e-2
+    mass = rng.random(n) ** 3 + 1e-6
+    return pos, vel, mass
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fp32_restatement_tracks_fp64_on_random_clouds(seed):
+    """Beyond the golden vectors: on random clouds the FP32 torch restatement stays within the FP32 conditioning
+    bound of the FP64 C oracle, for accelerations (2e-7 * kappa, floor 2e-6) and for both energies."""
+    n = [2, 7, 50, 200, 333, 1000, 1500, 64][seed]
+    softening = [0.01, 0.1][seed % 2]
+    pos, vel, mass = _random_system(seed, n)
+    a32 = oracle.accelerations(pos, mass, 0.7, softening).numpy()
+    a64, kappa = c_oracle.accelerations_cond_f64(pos, mass, 0.7, softening, np.arange(n))
+    err = rel_rows(a32, a64)
+    assert np.all(err <= np.maximum(2e-6, 2e-7 * kappa)), (err.max(), kappa.max())
+    u32, k32 = oracle.energies(pos, vel, mass, 0.7, softening)
+    u64, k64 = c_oracle.energies_f64(pos, vel, mass, 0.7, softening)
+    assert abs(u32 - u64) <= 1e-5 * abs(u64) and abs(k32 - k64) <= 1e-5 * abs(k64)
+
+
+def test_condition_number_oracle_matches_plain_accelerations():
+    pos, vel, mass = _random_system(3, 120)
+    rows = np.array([0, 5, 119])
+    acc, kappa = c_oracle.accelerations_cond_f64(pos, mass, 1.0, 0.05, rows)
+    full = c_oracle.accelerations_f64(pos, mass, 1.0, 0.05)
+    np.testing.assert_allclose(acc, full[rows], rtol=1e-14)
+    assert np.all(kappa >= 1.0 - 1e-12)  # a 1-norm over a norm of the sum is never below one
