@@ -86,6 +86,25 @@ int nbody_integrate_f32(int integrator, float* pos, float* vel, float* acc, cons
 int nbody_energies_f32(const float* pos, const float* vel, const float* mass, int n, float g, float eps,
                        double* out_uk, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Total linear and angular momentum of a state: out = 6 device doubles (px, py, pz, lx, ly, lz) with p = sum m v and
+ * l = sum m (x cross v), FP64 sums in a fixed order. `pos` may be NULL (then l = 0). The reference has no momentum
+ * function; its momentum DRIFT is one of the parity metrics, evaluated on the device here. */
+int nbody_momentum_f32(const float* pos, const float* vel, const float* mass, int n, double* out, void* stream);
+
+/* ---------------------------------------------------------------- rollout integrator (force slot left open) -- */
+
+/* The kick-drift-kick update that the surrogate-model rollout wraps around `model.predict`
+ * (trainer.py:217-226 Trainer.step, gnn.py:223-232 GraphModel.step), i.e. LeapFrogSimulator.step
+ * (simulation.py:164-170) with the accelerations supplied by the caller:
+ *   nbody_kick_drift_f32:  vel_out = vel + half_dt*acc ; pos_out = pos + dt*vel_out      (trainer.py:219-221)
+ *   ... caller evaluates acc_new = predict(pos_out, ...) ...                             (trainer.py:223)
+ *   nbody_kick_f32:        vel_out = vel + half_dt*acc_new                               (trainer.py:225)
+ * All arrays are (n,3) device floats; outputs may alias the matching inputs (in-place) or be distinct (the reference
+ * returns new tensors). Each update is a separately rounded multiply and add, as torch evaluates it. n = 0 is a no-op. */
+int nbody_kick_drift_f32(const float* pos, const float* vel, const float* acc, float* pos_out, float* vel_out, int n,
+                         float dt, float half_dt, void* stream);
+int nbody_kick_f32(const float* vel, const float* acc, float* vel_out, int n, float half_dt, void* stream);
+
 /* ---------------------------------------------------------------- sharded (multi-GPU) path ------------------- */
 
 /* i-sharded building blocks: every rank holds the full body array (x,y,z,m float4 x n_total) and the state of

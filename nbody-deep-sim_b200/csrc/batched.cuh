@@ -147,7 +147,12 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
             a[k][c] = (p.mode == MODE_LEAPFROG) ? gacc[3 * idx[k] + c] : 0.f;
         }
     }
-    __syncthreads();
+    // Every CTA of the cluster must be running before any of them writes into a peer's shared memory (publish()),
+    // and a peer's initial load of buf0 must have finished before it is read: a cluster-wide barrier does both.
+    if (csize > 1)
+        cluster.sync();
+    else
+        __syncthreads();
 
     float4* cur = buf0;
     float4* nxt = buf1;

@@ -14,6 +14,7 @@
 #include "batched.cuh"
 #include "energy.cuh"
 #include "force.cuh"
+#include "integrator.cuh"
 #include "probe.cuh"
 
 namespace {
@@ -48,6 +49,72 @@ int fail(int status, const char* fmt, ...) {
             return fail(NBODY_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, \
                         __LINE__);                                                                         \
     } while (0)
+
+// Restores the calling thread's current CUDA device on scope exit (the *_host_f32 entry points and the probe select
+// the device they are given).
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&saved) != cudaSuccess) saved = -1;
+    }
+    ~DeviceGuard() {
+        if (saved >= 0) cudaSetDevice(saved);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// Per-step device times from a bounded ring of CUDA event pairs: step s uses pair s % kRing, and before a pair is
+// reused the step that still owns it is read out (the host then blocks only on work that is kRing steps old).
+// All events are destroyed on scope exit, whatever path leaves the caller.
+class StepTimer {
+   public:
+    static constexpr int kRing = 256;
+    ~StepTimer() {
+        for (cudaEvent_t e : ev_) cudaEventDestroy(e);
+    }
+    int init(float* out_ms, int steps, cudaStream_t stream) {
+        out_ = out_ms, stream_ = stream;
+        if (!out_) return NBODY_OK;
+        pairs_ = steps < kRing ? steps : kRing;
+        ev_.reserve(size_t(2) * pairs_);
+        for (int i = 0; i < 2 * pairs_; ++i) {
+            cudaEvent_t e;
+            NB_CUDA(cudaEventCreate(&e));
+            ev_.push_back(e);
+        }
+        return NBODY_OK;
+    }
+    int begin(int step) {
+        if (!out_) return NBODY_OK;
+        if (step >= pairs_)
+            if (int st = drain(step - pairs_ + 1)) return st;
+        NB_CUDA(cudaEventRecord(ev_[2 * (step % pairs_)], stream_));
+        return NBODY_OK;
+    }
+    int end(int step) {
+        if (!out_) return NBODY_OK;
+        NB_CUDA(cudaEventRecord(ev_[2 * (step % pairs_) + 1], stream_));
+        ended_ = step + 1;
+        return NBODY_OK;
+    }
+    // Reads every step timed so far; synchronises with the last one.
+    int finish() { return out_ ? drain(ended_) : NBODY_OK; }
+
+   private:
+    int drain(int upto_step) {  // reads steps [read_, upto_step)
+        for (; read_ < upto_step; ++read_) {
+            const int k = 2 * (read_ % pairs_);
+            NB_CUDA(cudaEventSynchronize(ev_[k + 1]));
+            NB_CUDA(cudaEventElapsedTime(&out_[read_], ev_[k], ev_[k + 1]));
+        }
+        return NBODY_OK;
+    }
+    std::vector<cudaEvent_t> ev_;
+    float* out_ = nullptr;
+    int pairs_ = 0, ended_ = 0, read_ = 0;
+    cudaStream_t stream_ = nullptr;
+};
 
 // ------------------------------------------------------------------------------------------------ device info
 
@@ -155,6 +222,8 @@ constexpr size_t kCounterBytes = 64 * 1024;        // up to 16384 i-tiles
 constexpr size_t kEnergyPartialBytes = 512 * 1024;  // up to 65536 CTAs
 
 // Carves the workspace; with base == nullptr only sizes it. `own_bodies` = the body arrays live in the workspace.
+// The counters and the energy scratch sit at offsets that do not depend on the launch plan, so every entry point
+// finds them in the same place whatever `n_parts` the workspace was sized for; the split-j partials come last.
 Workspace carve(void* base, int n_local, int n_total, int n_parts, bool own_bodies) {
     Workspace w{};
     size_t off = 0;
@@ -168,12 +237,12 @@ Workspace carve(void* base, int n_local, int n_total, int n_parts, bool own_bodi
         w.bodies[1] = static_cast<float4*>(take(size_t(n_total) * sizeof(float4)));
         w.vhalf = static_cast<float*>(take(size_t(n_local) * 3 * sizeof(float)));
     }
+    w.counters = static_cast<unsigned*>(take(kCounterBytes));
+    w.energy_partial = static_cast<double*>(take(kEnergyPartialBytes));
     w.partial_stride = int(align_up(size_t(n_local), 32));
     const int j_len = n_total / n_parts > 0 ? n_total / n_parts : 1;
     const int slots = plan_force(n_local, j_len).splits * n_parts;
     w.partial = static_cast<double*>(take(size_t(slots) * 3 * w.partial_stride * sizeof(double)));
-    w.counters = static_cast<unsigned*>(take(kCounterBytes));
-    w.energy_partial = static_cast<double*>(take(kEnergyPartialBytes));
     w.total = off;
     return w;
 }
@@ -207,11 +276,16 @@ int launch_force_shape(const ForceParams& p, int i_tiles, int splits, bool exact
     return NBODY_OK;
 }
 
+// The self term is d = 0 times w = eps2^(-3/2) * m: exactly zero as long as w is finite. For a tiny softening w
+// overflows (eps2 = 1e-30 gives 1e45 * m) and 0 * inf = NaN, where the reference's fill_diagonal_(0)
+// (simulation.py:85) still returns a finite sum; below 1e-16 (w <= 1e24 * m) the index-masked variant is taken. It
+// also covers eps2 below FLT_MIN, which MUFU.RSQ flushes to zero.
+bool needs_exact_diag(float eps2) { return !(eps2 >= 1e-16f); }
+
 int launch_force(const Plan& pl, const ForceParams& p, cudaStream_t stream) {
     if (size_t(pl.i_tiles) * sizeof(unsigned) > kCounterBytes)
         return fail(NBODY_ERR_UNSUPPORTED, "force: %d i-tiles exceed the %zu-byte counter scratch", pl.i_tiles, kCounterBytes);
-    // softening^2 below the smallest normal float is flushed by MUFU.RSQ: take the index-masked variant.
-    const bool exact_diag = !(p.eps2 >= 1.17549435e-38f);
+    const bool exact_diag = needs_exact_diag(p.eps2);
     if (pl.large)
         return launch_force_shape<kLarge.pairs, kLarge.warps, kLarge.min_blocks, kLarge.tile_j, kLarge.unroll>(
             p, pl.i_tiles, pl.splits, exact_diag, stream);
@@ -303,7 +377,11 @@ int nbody_plan_f32(int n_local, int j_len, int* shape_large, int* i_tiles, int* 
 
 size_t nbody_shard_workspace_bytes(int n_local, int n_total, int n_parts) {
     if (n_local < 1 || n_total < n_local || n_parts < 1) return 0;
-    return workspace_bytes_impl(n_local, n_total, n_parts, false);
+    // A simulator sized for an n_parts-launch step also makes single-sweep calls (initial force, energies): the
+    // planner may pick more splits for one sweep than for n_parts shorter ones, so size for whichever is larger.
+    const size_t a = workspace_bytes_impl(n_local, n_total, n_parts, false);
+    const size_t b = workspace_bytes_impl(n_local, n_total, 1, false);
+    return a > b ? a : b;
 }
 
 int nbody_accel_f32(const float* pos, const float* mass, float* acc, int n, float g, float eps2, void* workspace,
@@ -358,71 +436,46 @@ int nbody_integrate_f32(int integrator, float* pos, float* vel, float* acc, cons
         return (traj && recorded(s)) ? traj + (slot_of(s) * 3 + which) * plane : nullptr;
     };
 
-    std::vector<cudaEvent_t> events;
-    if (step_ms) {
-        events.resize(size_t(steps) + 1);
-        for (auto& e : events) NB_CUDA(cudaEventCreate(&e));
-    }
-    auto cleanup = [&]() {
-        for (auto& e : events) cudaEventDestroy(e);
-    };
+    StepTimer timer;
+    if (int st = timer.init(step_ms, steps, stream)) return st;
 
-    int st = NBODY_OK;
-    do {
-        PrepParams pp{};
-        pp.n = n, pp.i_begin = 0, pp.mode = mode, pp.dt = dt, pp.half_dt = half_dt;
-        pp.mass = mass, pp.pos = pos, pp.vel = vel, pp.acc = acc, pp.vhalf = w.vhalf, pp.bodies = w.bodies[0];
-        pp.rec_pos = (mode == MODE_LEAPFROG) ? traj_plane(0, 0) : nullptr;
-        if ((st = launch_prep(pp, stream))) break;
-        if (pl.splits > 1) {
-            cudaError_t e = cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream);
-            if (e != cudaSuccess) {
-                st = fail(NBODY_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-                break;
-            }
-        }
-        if (step_ms) cudaEventRecord(events[0], stream);
+    PrepParams pp{};
+    pp.n = n, pp.i_begin = 0, pp.mode = mode, pp.dt = dt, pp.half_dt = half_dt;
+    pp.mass = mass, pp.pos = pos, pp.vel = vel, pp.acc = acc, pp.vhalf = w.vhalf, pp.bodies = w.bodies[0];
+    pp.rec_pos = (mode == MODE_LEAPFROG) ? traj_plane(0, 0) : nullptr;
+    if (int st = launch_prep(pp, stream)) return st;
+    if (pl.splits > 1) NB_CUDA(cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream));
 
-        for (int s = 0; s < steps && st == NBODY_OK; ++s) {
-            const int cur = s & 1;
-            ForceParams fp{};
-            fp.bodies = w.bodies[cur], fp.bodies_next = w.bodies[cur ^ 1];
-            fp.j_begin = 0, fp.j_end = n, fp.i_begin = 0, fp.i_count = n;
-            fp.eps2 = eps2, fp.g = g;
-            fp.partial = w.partial, fp.partial_stride = w.partial_stride, fp.split_offset = 0;
-            fp.splits_total = pl.splits, fp.counters = w.counters;
-            fp.mode = mode, fp.dt = dt, fp.half_dt = half_dt;
-            fp.pos = pos, fp.vel = vel, fp.acc = acc, fp.vhalf = w.vhalf;
-            fp.rec_vel = traj_plane(s, 1), fp.rec_acc = traj_plane(s, 2);
-            if (mode == MODE_LEAPFROG) {
-                fp.do_next = (s + 1 < steps);
-                fp.rec_pos = fp.do_next ? traj_plane(s + 1, 0) : nullptr;  // x of state s+1 is produced here
-            } else {
-                fp.do_next = 1;
-                fp.rec_pos = traj_plane(s, 0);
-            }
-            if ((st = launch_force(pl, fp, stream))) break;
-            if (energies && recorded(s)) {
-                // positions of state s: the buffer this launch consumed (leapfrog) or produced (euler)
-                const float4* state_bodies = (mode == MODE_LEAPFROG) ? w.bodies[cur] : w.bodies[cur ^ 1];
-                if ((st = launch_energy(state_bodies, vel, n, 0, n, g, eps, w.energy_partial,
-                                        energies + 2 * slot_of(s), dev->sms, stream)))
-                    break;
-            }
-            if (step_ms) cudaEventRecord(events[size_t(s) + 1], stream);
-        }
-    } while (0);
-
-    if (st == NBODY_OK && step_ms) {
-        cudaError_t e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) {
-            st = fail(NBODY_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+    for (int s = 0; s < steps; ++s) {
+        const int cur = s & 1;
+        if (int st = timer.begin(s)) return st;
+        ForceParams fp{};
+        fp.bodies = w.bodies[cur], fp.bodies_next = w.bodies[cur ^ 1];
+        fp.j_begin = 0, fp.j_end = n, fp.i_begin = 0, fp.i_count = n;
+        fp.eps2 = eps2, fp.g = g;
+        fp.partial = w.partial, fp.partial_stride = w.partial_stride, fp.split_offset = 0;
+        fp.splits_total = pl.splits, fp.counters = w.counters;
+        fp.mode = mode, fp.dt = dt, fp.half_dt = half_dt;
+        fp.pos = pos, fp.vel = vel, fp.acc = acc, fp.vhalf = w.vhalf;
+        fp.rec_vel = traj_plane(s, 1), fp.rec_acc = traj_plane(s, 2);
+        if (mode == MODE_LEAPFROG) {
+            fp.do_next = (s + 1 < steps);
+            fp.rec_pos = fp.do_next ? traj_plane(s + 1, 0) : nullptr;  // x of state s+1 is produced here
         } else {
-            for (int s = 0; s < steps; ++s) cudaEventElapsedTime(&step_ms[s], events[s], events[size_t(s) + 1]);
+            fp.do_next = 1;
+            fp.rec_pos = traj_plane(s, 0);
+        }
+        if (int st = launch_force(pl, fp, stream)) return st;
+        if (int st = timer.end(s)) return st;  // step_ms = the force/integrator launch alone, as simulation.py:127-129
+        if (energies && recorded(s)) {
+            // positions of state s: the buffer this launch consumed (leapfrog) or produced (euler)
+            const float4* state_bodies = (mode == MODE_LEAPFROG) ? w.bodies[cur] : w.bodies[cur ^ 1];
+            if (int st = launch_energy(state_bodies, vel, n, 0, n, g, eps, w.energy_partial, energies + 2 * slot_of(s),
+                                       dev->sms, stream))
+                return st;
         }
     }
-    cleanup();
-    return st;
+    return timer.finish();
 }
 
 int nbody_energies_f32(const float* pos, const float* vel, const float* mass, int n, float g, float eps,
@@ -510,8 +563,9 @@ int nbody_shard_energies_f32(const float* bodies, const float* vel, int n_total,
     const DeviceInfo* dev;
     if (int st = current_device_info(&dev)) return st;
     Workspace w = carve(workspace, n_local, n_total, 1, false);
-    if (w.total > workspace_bytes)
-        return fail(NBODY_ERR_WORKSPACE, "shard_energies: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    const size_t need = size_t(reinterpret_cast<char*>(w.energy_partial) - static_cast<char*>(workspace)) + kEnergyPartialBytes;
+    if (need > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "shard_energies: workspace %zu < %zu bytes", workspace_bytes, need);
     return launch_energy(reinterpret_cast<const float4*>(bodies), vel, n_total, i_begin, n_local, g, eps,
                          w.energy_partial, out_uk, dev->sms, static_cast<cudaStream_t>(stream_));
 }
@@ -557,7 +611,7 @@ static int batched_launch(int mode, float* pos, float* vel, float* acc, const fl
     p.n = n, p.mode = mode, p.steps = steps, p.record_every = record_every > 0 ? record_every : 1;
     p.g = g, p.eps2 = eps2, p.dt = dt, p.half_dt = half_dt;
     p.mass = mass, p.pos = pos, p.vel = vel, p.acc = acc, p.traj = traj, p.n_systems = n_systems;
-    const bool exact = !(eps2 >= 1.17549435e-38f);
+    const bool exact = needs_exact_diag(eps2);
     if (n <= 64) return batched_launch_shape<1, 32>(p, 1, exact, stream);
     if (n <= 128) return batched_launch_shape<1, 64>(p, 1, exact, stream);
     if (n <= 256) return batched_launch_shape<1, 128>(p, 1, exact, stream);
@@ -646,6 +700,7 @@ int nbody_accel_host_f32(const float* pos, const float* mass, float* acc, int n,
     if (n < 1) return fail(NBODY_ERR_INVALID_ARGUMENT, "accel_host: n = %d", n);
     if (device < 0 || device >= kMaxDevices) return fail(NBODY_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", device);
     std::lock_guard<std::mutex> lock(g_host_mutex[device]);
+    DeviceGuard restore_device;
     const size_t b3 = align_up(size_t(n) * 12, 256), b1 = align_up(size_t(n) * 4, 256);
     const size_t ws = nbody_workspace_bytes(n, n);
     HostCache* c;
@@ -675,6 +730,7 @@ int nbody_integrate_host_f32(int integrator, float* pos, float* vel, float* acc,
         return fail(NBODY_ERR_INVALID_ARGUMENT, "integrate_host: record_every = %d", record_every);
     if (device < 0 || device >= kMaxDevices) return fail(NBODY_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", device);
     std::lock_guard<std::mutex> lock(g_host_mutex[device]);
+    DeviceGuard restore_device;
     const size_t slots = (traj || energies) ? size_t(steps / record_every) : 0;
     const size_t b3 = align_up(size_t(n) * 12, 256), b1 = align_up(size_t(n) * 4, 256);
     const size_t b_traj = traj ? align_up(slots * 3 * size_t(n) * 12, 256) : 0;
@@ -711,6 +767,7 @@ int nbody_integrate_host_f32(int integrator, float* pos, float* vel, float* acc,
 }
 
 int nbody_host_cache_release(void) {
+    DeviceGuard restore_device;
     for (int d = 0; d < kMaxDevices; ++d) {
         std::lock_guard<std::mutex> lock(g_host_mutex[d]);
         HostCache& c = g_host[d];
@@ -725,37 +782,108 @@ int nbody_host_cache_release(void) {
 
 // ------------------------------------------------------------------------------------------------ measurement
 
+namespace {
+struct ProbeScratch {  // frees whatever was created, on every path out of the probe
+    float* out = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t stream = nullptr;
+    ~ProbeScratch() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (out) cudaFree(out);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+}  // namespace
+
 int nbody_probe_fp32_peak(int device, int packed, double* tflops) {
     if (!tflops) return fail(NBODY_ERR_INVALID_ARGUMENT, "probe: null pointer");
+    if (device < 0 || device >= kMaxDevices) return fail(NBODY_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", device);
+    DeviceGuard restore_device;
     NB_CUDA(cudaSetDevice(device));
     const DeviceInfo* dev;
     if (int st = current_device_info(&dev)) return st;
-    float* d_out;
-    NB_CUDA(cudaMalloc(&d_out, 256));
-    cudaEvent_t e0, e1;
-    NB_CUDA(cudaEventCreate(&e0));
-    NB_CUDA(cudaEventCreate(&e1));
+    ProbeScratch sc;
+    NB_CUDA(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
+    NB_CUDA(cudaMalloc(&sc.out, 256));
+    NB_CUDA(cudaEventCreate(&sc.e0));
+    NB_CUDA(cudaEventCreate(&sc.e1));
     const int blocks = dev->sms * 8, outer = 256;
     double best = 0.0;
     for (int rep = 0; rep < 6; ++rep) {  // first reps warm the clocks; keep the best
-        NB_CUDA(cudaEventRecord(e0, 0));
+        NB_CUDA(cudaEventRecord(sc.e0, sc.stream));
         if (packed)
-            fma_probe_kernel<true><<<blocks, 256>>>(d_out, outer, 1.0000001f, 1e-9f);
+            fma_probe_kernel<true><<<blocks, 256, 0, sc.stream>>>(sc.out, outer, 1.0000001f, 1e-9f);
         else
-            fma_probe_kernel<false><<<blocks, 256>>>(d_out, outer, 1.0000001f, 1e-9f);
+            fma_probe_kernel<false><<<blocks, 256, 0, sc.stream>>>(sc.out, outer, 1.0000001f, 1e-9f);
         NB_LAUNCH_CHECK();
-        NB_CUDA(cudaEventRecord(e1, 0));
-        NB_CUDA(cudaEventSynchronize(e1));
+        NB_CUDA(cudaEventRecord(sc.e1, sc.stream));
+        NB_CUDA(cudaEventSynchronize(sc.e1));
         float ms = 0.f;
-        NB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        NB_CUDA(cudaEventElapsedTime(&ms, sc.e0, sc.e1));
         const double flops = double(blocks) * 256 * double(outer) * kProbeInner * kProbeChains * 2 /*lanes*/ * 2 /*fma*/;
         const double tf = flops / (double(ms) * 1e-3) / 1e12;
         if (tf > best) best = tf;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d_out);
     *tflops = best;
+    return NBODY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ rollout integrator
+
+namespace {
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+int elementwise_grid(long long work_items, int sms) {
+    long long blocks = (work_items + 255) / 256;
+    const long long cap = (long long)sms * 8;  // grid-stride: a few CTAs per SM saturate HBM
+    if (blocks > cap) blocks = cap;
+    return int(blocks < 1 ? 1 : blocks);
+}
+}  // namespace
+
+int nbody_kick_drift_f32(const float* pos, const float* vel, const float* acc, float* pos_out, float* vel_out, int n,
+                         float dt, float half_dt, void* stream_) {
+    if (!pos || !vel || !acc || !pos_out || !vel_out) return fail(NBODY_ERR_INVALID_ARGUMENT, "kick_drift: null pointer");
+    if (n < 0) return fail(NBODY_ERR_INVALID_ARGUMENT, "kick_drift: n = %d", n);
+    if (n == 0) return NBODY_OK;
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    KickDriftParams p{(long long)n * 3, dt, half_dt, pos, vel, acc, pos_out, vel_out};
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool vec = p.count % 4 == 0 && aligned16(pos) && aligned16(vel) && aligned16(acc) && aligned16(pos_out) && aligned16(vel_out);
+    if (vec)
+        kick_drift_kernel<true><<<elementwise_grid(p.count / 4, dev->sms), 256, 0, stream>>>(p);
+    else
+        kick_drift_kernel<false><<<elementwise_grid(p.count, dev->sms), 256, 0, stream>>>(p);
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+int nbody_kick_f32(const float* vel, const float* acc, float* vel_out, int n, float half_dt, void* stream_) {
+    if (!vel || !acc || !vel_out) return fail(NBODY_ERR_INVALID_ARGUMENT, "kick: null pointer");
+    if (n < 0) return fail(NBODY_ERR_INVALID_ARGUMENT, "kick: n = %d", n);
+    if (n == 0) return NBODY_OK;
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    KickParams p{(long long)n * 3, half_dt, vel, acc, vel_out};
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool vec = p.count % 4 == 0 && aligned16(vel) && aligned16(acc) && aligned16(vel_out);
+    if (vec)
+        kick_kernel<true><<<elementwise_grid(p.count / 4, dev->sms), 256, 0, stream>>>(p);
+    else
+        kick_kernel<false><<<elementwise_grid(p.count, dev->sms), 256, 0, stream>>>(p);
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+int nbody_momentum_f32(const float* pos, const float* vel, const float* mass, int n, double* out, void* stream_) {
+    if (!vel || !mass || !out) return fail(NBODY_ERR_INVALID_ARGUMENT, "momentum: null pointer");
+    if (n < 1) return fail(NBODY_ERR_INVALID_ARGUMENT, "momentum: n = %d", n);
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    MomentumParams p{n, pos, vel, mass, out};
+    momentum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+    NB_LAUNCH_CHECK();
     return NBODY_OK;
 }
 

@@ -50,6 +50,9 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "nbody_momentum_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "nbody_kick_drift_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
+    "nbody_kick_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     "nbody_shard_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "nbody_shard_prepare_f32": (
         c_int,

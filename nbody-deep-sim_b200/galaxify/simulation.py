@@ -137,26 +137,28 @@ class BaseSimulator:
     def _persistent(self) -> bool:
         return 0 < self.n <= PERSISTENT_MAX_N
 
-    def _integrate_persistent(self, steps, record_every, traj, energies):
-        """All `steps` in one launch of the batched kernel (one system), then the energies of the recorded slots."""
+    def _integrate_persistent(self, steps, record_every, traj, energies, step_ms):
+        """All `steps` in one launch of the batched kernel (one system), then the energies of the recorded slots.
+        step_ms receives the mean device time of a step (the steps never leave the kernel); like the tiled path and
+        the reference (simulation.py:127-129) it covers the integrator only, not the energy evaluation."""
         s = self._scalars()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.device(self._device_index):
+            start.record()
             _native.call("nbody_batched_integrate_f32", self._integrator, _ptr(self.positions), _ptr(self.velocities),
                          _ptr(self.accelerations), _ptr(self.masses), 1, self.n, s["g"], s["eps2"], s["dt"],
                          s["half_dt"], steps, record_every, _ptr(traj), self._stream())
+            end.record()
             if energies is not None and traj is not None:
                 _native.call("nbody_traj_energies_f32", _ptr(traj), _ptr(self.masses), steps // record_every, 1,
                              self.n, s["g"], s["eps"], _ptr(energies), self._stream())
+        if step_ms is not None:
+            end.synchronize()
+            step_ms[:] = start.elapsed_time(end) / max(steps, 1)
 
     def _integrate(self, steps, record_every, traj, energies, step_ms):
         if self._persistent():
-            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            start.record()
-            self._integrate_persistent(steps, record_every, traj, energies)
-            end.record()
-            if step_ms is not None:  # the steps run inside one kernel: report the mean
-                end.synchronize()
-                step_ms[:] = start.elapsed_time(end) / max(steps, 1)
+            self._integrate_persistent(steps, record_every, traj, energies, step_ms)
             return
         s = self._scalars()
         ws = self._ws()
@@ -207,11 +209,26 @@ class BaseSimulator:
         u, k = out.tolist()
         return u, k
 
+    def compute_momentum(self):
+        """(p, l): total linear momentum sum m v and angular momentum sum m (x cross v) as two float64 numpy arrays of
+        shape (3,), summed on the device in FP64. An addition (the reference has no momentum function); its drift is
+        one of the conservation metrics of SURVEY.md 8a."""
+        if self.n == 0:
+            return np.zeros(3), np.zeros(3)
+        out = torch.empty(6, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self._device_index):
+            _native.call("nbody_momentum_f32", _ptr(self.positions), _ptr(self.velocities), _ptr(self.masses), self.n,
+                         _ptr(out), self._stream())
+        v = out.cpu().numpy()
+        return v[:3].copy(), v[3:].copy()
+
     def run(self, steps: int, record_every: int = 1) -> list[SimulationState]:
         """Runs `steps` steps and returns the recorded states (simulation.py:117-146).
 
         State k describes the system after step k+1; the initial state is not recorded; `step` is 0-based.
         With record_every > 1 (an addition) only every record_every-th step is recorded.
+        The tensors of the returned states are views into one pinned host buffer per chunk (up to TRAJ_CHUNK_BYTES):
+        keeping any one of them alive keeps its chunk alive; `.clone()` a state's tensors to hold on to them alone.
         """
         if record_every < 1:
             raise ValueError("record_every must be >= 1")
