@@ -133,6 +133,32 @@ int nbody_shard_force_f32(int integrator, const float* bodies, float* bodies_nex
 int nbody_shard_energies_f32(const float* bodies, const float* vel, int n_total, int i_begin, int n_local, float g,
                              float eps, double* out_uk, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Pair (Newton's-third-law) building blocks of the sharded step, for systems of at least nbody_pair_min_bodies()
+ * bodies: every unordered pair of bodies is evaluated once over ALL ranks. Rank `my_slot` evaluates the triangle of
+ * its own slot, the full rectangles against the next floor((P-1)/2) slots and, for even P, half of the rectangle
+ * against the opposite slot; forces and reactions are accumulated (RED.ADD.F64) into `acc64`, an array of
+ * n_slots*slot_size*3 doubles laid out like the body array, which therefore holds partial sums for bodies of OTHER
+ * slots too: the caller sums the arrays over ranks slot by slot (a reduce-scatter) and hands its own slot's sums to
+ * nbody_shard_pair_finish_f32, which applies fl32(G) and the integrator epilogue exactly as nbody_shard_force_f32's
+ * last part does, writes the rank's slice of bodies_next, and clears acc_own plus `acc_clear` (pass the full acc64
+ * there when it is a different buffer from acc_own; NULL/0 otherwise) for the next step.
+ *   plan : once per simulator (and again if n or the layout changes); split_phases != 0 keeps the own-slot triangle
+ *          (phase 0, needs no remote data: run it while the all-gather is in flight) apart from the cross-slot
+ *          rectangles (phase 1); split_phases == 0 puts everything into phase 0.
+ *   force: one launch per phase, persistent CTAs pulling (I-tile, J-run) items from a counter in the workspace.
+ * `n` is the number of real bodies; slot s holds bodies [s*slot_size, min(n, (s+1)*slot_size)). The workspace content
+ * (item lists, counters) must be preserved between plan, force and finish. No reference counterpart. */
+int nbody_pair_min_bodies(void);
+size_t nbody_shard_pair_workspace_bytes(int n_slots, int slot_size);
+int nbody_shard_pair_plan_f32(int n, int n_slots, int slot_size, int my_slot, int split_phases, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int nbody_shard_pair_force_f32(int phase, const float* bodies, int n_slots, int slot_size, float eps2, double* acc64,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int nbody_shard_pair_finish_f32(int integrator, const float* bodies, float* bodies_next, int i_begin, int n_local,
+                                double* acc_own, double* acc_clear, long long acc_clear_count, float* pos, float* vel,
+                                float* acc, float* vhalf, float g, float dt, float half_dt, int do_next, int n_slots,
+                                int slot_size, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- batched many-small-systems path ------------ */
 
 /* `n_systems` independent systems of `n` bodies each (n <= nbody_batched_max_n()), all stepped `steps` times

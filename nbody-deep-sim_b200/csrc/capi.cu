@@ -15,6 +15,7 @@
 #include "energy.cuh"
 #include "force.cuh"
 #include "integrator.cuh"
+#include "pair.cuh"
 #include "probe.cuh"
 
 namespace {
@@ -216,8 +217,37 @@ struct Workspace {
     unsigned* counters;
     double* energy_partial;
     int partial_stride;
+    // pair path (n_total >= kPairMinBodies): FP64 accumulators, item list, item count, item counters
+    double* acc64;
+    PairItem* items;
+    int* n_items;
+    unsigned* pair_counters;
+    int max_items;
     size_t total;
 };
+
+// Pair kernel shape (tools/tune_pair.cu, profiles/r2_tune_pair.log): 384 threads x 4 i-bodies, 1 CTA/SM.
+constexpr int kPairPairs = 2, kPairWarps = 12, kPairMinBlocks = 1;
+constexpr int kPairTileI = kPairWarps * 32 * 2 * kPairPairs;  // 1536
+constexpr int kPairTileJ = kPairWarps * 32;                   // 384
+// Systems at least this large take the pair path (below it there are too few (I-tile, J-tile) units to balance
+// 148 persistent CTAs, and force.cuh's deterministic split-j reduction is kept).
+constexpr int kPairMinBodies = 65536;
+constexpr int kPairCounters = 4;
+
+// J-tiles per symmetric item: about 48 items per SM, so that the tail of the dynamic schedule (one item) stays ~2%,
+// but items long enough to amortise their prologue (i-body load, pipeline refill, i-sum flush).
+int pair_chunk_tiles(long long sym_tile_units) {
+    long long c = sym_tile_units / (kPlanSms * 48LL);
+    if (c < 1) c = 1;
+    if (c > 32) c = 32;
+    return int(c);
+}
+long long tiles_of(long long bodies, int tile) { return (bodies + tile - 1) / tile; }
+// Upper bound of the item count of one block with i_len x j_len bodies.
+long long pair_block_items(long long i_len, long long j_len, int chunk_tiles) {
+    return tiles_of(i_len, kPairTileI) * (tiles_of(j_len, kPairTileJ) / chunk_tiles + 3);
+}
 constexpr size_t kCounterBytes = 64 * 1024;        // up to 16384 i-tiles
 constexpr size_t kEnergyPartialBytes = 512 * 1024;  // up to 65536 CTAs
 
@@ -243,6 +273,14 @@ Workspace carve(void* base, int n_local, int n_total, int n_parts, bool own_bodi
     const int j_len = n_total / n_parts > 0 ? n_total / n_parts : 1;
     const int slots = plan_force(n_local, j_len).splits * n_parts;
     w.partial = static_cast<double*>(take(size_t(slots) * 3 * w.partial_stride * sizeof(double)));
+    if (own_bodies && n_total >= kPairMinBodies) {
+        const long long units = tiles_of(n_total, kPairTileI) * tiles_of(n_total, kPairTileJ) / 2;
+        w.max_items = int(pair_block_items(n_total, n_total, pair_chunk_tiles(units)));
+        w.acc64 = static_cast<double*>(take(size_t(n_total) * 3 * sizeof(double)));
+        w.items = static_cast<PairItem*>(take(size_t(w.max_items) * sizeof(PairItem)));
+        w.n_items = static_cast<int*>(take(256));
+        w.pair_counters = static_cast<unsigned*>(take(256));
+    }
     w.total = off;
     return w;
 }
@@ -324,6 +362,56 @@ int launch_energy(const float4* bodies, const float* vel, int n_total, int i_beg
     return NBODY_OK;
 }
 
+bool use_pair(int n_total, float eps2) { return n_total >= kPairMinBodies && !needs_exact_diag(eps2); }
+
+int launch_pair_plan(const PairBlock* blocks, int n_blocks, int chunk_tiles, PairItem* items, int max_items, int* n_items,
+                     cudaStream_t stream) {
+    if (n_blocks < 1 || n_blocks > kMaxPairBlocks) return fail(NBODY_ERR_INVALID_ARGUMENT, "pair plan: %d blocks", n_blocks);
+    PairPlanParams pp{};
+    for (int b = 0; b < n_blocks; ++b) pp.blocks[b] = blocks[b];
+    pp.n_blocks = n_blocks, pp.tile_i = kPairTileI, pp.tile_j = kPairTileJ, pp.chunk_tiles = chunk_tiles;
+    pp.items = items, pp.max_items = max_items, pp.n_items = n_items;
+    pair_plan_kernel<<<1, 256, 0, stream>>>(pp);
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+int launch_pair(const PairParams& p, int sms, cudaStream_t stream) {
+    auto k = pair_kernel<kPairPairs, kPairWarps, kPairMinBlocks>;
+    const size_t smem = PairRing<kPairWarps>::smem_bytes();
+    if (int st = set_smem(k, smem)) return st;
+    k<<<sms * kPairMinBlocks, kPairWarps * 32, smem, stream>>>(p);
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+int launch_finish(const FinishParams& p, int sms, cudaStream_t stream) {
+    long long work = p.f.i_count > p.zero_count / 3 ? p.f.i_count : p.zero_count / 3;
+    long long blocks = (work + 255) / 256;
+    if (blocks > sms * 8LL) blocks = sms * 8LL;
+    finish_kernel<<<int(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(p);
+    NB_LAUNCH_CHECK();
+    return NBODY_OK;
+}
+
+// Plans the single-GPU pair path (one triangle over all n bodies) and clears its accumulators.
+int pair_begin_single(const Workspace& w, int n, cudaStream_t stream) {
+    NB_CUDA(cudaMemsetAsync(w.acc64, 0, size_t(n) * 3 * sizeof(double), stream));
+    NB_CUDA(cudaMemsetAsync(w.pair_counters, 0, kPairCounters * sizeof(unsigned), stream));
+    const PairBlock tri{0, n, 0, n, 1};
+    const long long units = tiles_of(n, kPairTileI) * tiles_of(n, kPairTileJ) / 2;
+    return launch_pair_plan(&tri, 1, pair_chunk_tiles(units), w.items, w.max_items, w.n_items, stream);
+}
+
+// One force evaluation + epilogue on the pair path: `fp` carries everything the epilogue needs (as for force_kernel).
+int pair_step_single(const Workspace& w, const ForceParams& fp, int sms, cudaStream_t stream) {
+    PairParams pp{fp.bodies, fp.eps2, w.items, w.n_items, w.pair_counters, w.acc64};
+    if (int st = launch_pair(pp, sms, stream)) return st;
+    FinishParams fin{};
+    fin.f = fp, fin.acc_own = w.acc64, fin.counters = w.pair_counters, fin.n_counters = kPairCounters;
+    return launch_finish(fin, sms, stream);
+}
+
 int mode_of(int integrator, int* mode) {
     if (integrator == NBODY_INTEGRATOR_LEAPFROG) {
         *mode = MODE_LEAPFROG;
@@ -400,7 +488,8 @@ int nbody_accel_f32(const float* pos, const float* mass, float* acc, int n, floa
     pp.n = n, pp.i_begin = 0, pp.mode = MODE_ACCEL, pp.mass = mass, pp.pos = const_cast<float*>(pos);
     pp.bodies = w.bodies[0];
     if (int st = launch_prep(pp, stream)) return st;
-    if (pl.splits > 1) NB_CUDA(cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream));
+    const bool pair = use_pair(n, eps2);
+    if (!pair && pl.splits > 1) NB_CUDA(cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream));
 
     ForceParams fp{};
     fp.bodies = w.bodies[0], fp.j_begin = 0, fp.j_end = n, fp.i_begin = 0, fp.i_count = n;
@@ -408,6 +497,10 @@ int nbody_accel_f32(const float* pos, const float* mass, float* acc, int n, floa
     fp.partial = w.partial, fp.partial_stride = w.partial_stride, fp.split_offset = 0, fp.splits_total = pl.splits;
     fp.counters = w.counters;
     fp.mode = MODE_ACCEL, fp.acc = acc;
+    if (pair) {
+        if (int st = pair_begin_single(w, n, stream)) return st;
+        return pair_step_single(w, fp, dev->sms, stream);
+    }
     return launch_force(pl, fp, stream);
 }
 
@@ -444,7 +537,12 @@ int nbody_integrate_f32(int integrator, float* pos, float* vel, float* acc, cons
     pp.mass = mass, pp.pos = pos, pp.vel = vel, pp.acc = acc, pp.vhalf = w.vhalf, pp.bodies = w.bodies[0];
     pp.rec_pos = (mode == MODE_LEAPFROG) ? traj_plane(0, 0) : nullptr;
     if (int st = launch_prep(pp, stream)) return st;
-    if (pl.splits > 1) NB_CUDA(cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream));
+    const bool pair = use_pair(n, eps2);
+    if (pair) {
+        if (int st = pair_begin_single(w, n, stream)) return st;
+    } else if (pl.splits > 1) {
+        NB_CUDA(cudaMemsetAsync(w.counters, 0, size_t(pl.i_tiles) * sizeof(unsigned), stream));
+    }
 
     for (int s = 0; s < steps; ++s) {
         const int cur = s & 1;
@@ -465,7 +563,7 @@ int nbody_integrate_f32(int integrator, float* pos, float* vel, float* acc, cons
             fp.do_next = 1;
             fp.rec_pos = traj_plane(s, 0);
         }
-        if (int st = launch_force(pl, fp, stream)) return st;
+        if (int st = pair ? pair_step_single(w, fp, dev->sms, stream) : launch_force(pl, fp, stream)) return st;
         if (int st = timer.end(s)) return st;  // step_ms = the force/integrator launch alone, as simulation.py:127-129
         if (energies && recorded(s)) {
             // positions of state s: the buffer this launch consumed (leapfrog) or produced (euler)
@@ -568,6 +666,170 @@ int nbody_shard_energies_f32(const float* bodies, const float* vel, int n_total,
         return fail(NBODY_ERR_WORKSPACE, "shard_energies: workspace %zu < %zu bytes", workspace_bytes, need);
     return launch_energy(reinterpret_cast<const float4*>(bodies), vel, n_total, i_begin, n_local, g, eps,
                          w.energy_partial, out_uk, dev->sms, static_cast<cudaStream_t>(stream_));
+}
+
+// ------------------------------------------------------------------------------------------------ sharded pair path
+
+}  // extern "C"
+
+namespace {
+struct ShardPairScratch {
+    PairItem* items[2];  // phase 0 (own triangle, or everything when not split), phase 1 (cross blocks)
+    int cap[2];
+    int* n_items;        // [2]
+    unsigned* counters;  // [kPairCounters]; phase p uses counters[p]
+    size_t total;
+};
+
+struct ShardPairGeometry {
+    PairBlock own;
+    PairBlock cross[kMaxPairBlocks];
+    int n_cross;
+    long long units;  // (I-tile, J-tile) units of this rank, for the chunk size
+};
+
+int slot_count(int n, int slot_size, int slot) {
+    const long long c = (long long)n - (long long)slot * slot_size;
+    return int(c < 0 ? 0 : (c > slot_size ? slot_size : c));
+}
+
+// Which part of the interaction matrix rank `r` of `P` evaluates (each unordered pair of bodies exactly once over all
+// ranks): the triangle of its own slot, the full rectangles against the next floor((P-1)/2) slots (cyclically), and for
+// even P one half of the rectangle against the opposite slot: the lower-numbered slot of that pair takes the first
+// half of its own I-tiles against all of the other slot, the higher-numbered one takes all of its bodies against the
+// second half of the lower slot.
+ShardPairGeometry shard_pair_geometry(int n, int P, int slot_size, int r) {
+    ShardPairGeometry g{};
+    const int lo = r * slot_size, cnt = slot_count(n, slot_size, r);
+    g.own = PairBlock{lo, lo + cnt, lo, lo + cnt, 1};
+    g.units = tiles_of(cnt, kPairTileI) * tiles_of(cnt, kPairTileJ) / 2;
+    auto add = [&](int i_lo, int i_hi, int j_lo, int j_hi) {
+        if (i_hi <= i_lo || j_hi <= j_lo) return;
+        g.cross[g.n_cross++] = PairBlock{i_lo, i_hi, j_lo, j_hi, 0};
+        g.units += tiles_of(i_hi - i_lo, kPairTileI) * tiles_of(j_hi - j_lo, kPairTileJ);
+    };
+    const int K = (P - 1) / 2;
+    for (int k = 1; k <= K; ++k) {
+        const int s = (r + k) % P;
+        add(lo, lo + cnt, s * slot_size, s * slot_size + slot_count(n, slot_size, s));
+    }
+    if (P % 2 == 0 && P > 1) {
+        const int s = (r + P / 2) % P;
+        const int low = r < s ? r : s;
+        const int cnt_low = slot_count(n, slot_size, low);
+        const int half = int(((tiles_of(cnt_low, kPairTileI) + 1) / 2) * kPairTileI);  // bodies in the first half of low's I-tiles
+        const int split = half < cnt_low ? half : cnt_low;
+        const int s_lo = s * slot_size, s_cnt = slot_count(n, slot_size, s);
+        if (r == low)
+            add(lo, lo + split, s_lo, s_lo + s_cnt);
+        else
+            add(lo, lo + cnt, s_lo + split, s_lo + s_cnt);
+    }
+    return g;
+}
+
+ShardPairScratch carve_shard_pair(void* base, int n_slots, int slot_size) {
+    ShardPairScratch w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    // capacities for the smallest chunk (1 tile): a bound for every chunk size the planner may pick
+    const long long own = pair_block_items(slot_size, slot_size, 1);
+    const long long cross = pair_block_items(slot_size, slot_size, 1) * ((n_slots - 1) / 2 + 1);
+    w.cap[0] = int(own + cross);  // phase 0 holds everything when the step is not split
+    w.cap[1] = int(cross);
+    w.items[0] = static_cast<PairItem*>(take(size_t(w.cap[0]) * sizeof(PairItem)));
+    w.items[1] = static_cast<PairItem*>(take(size_t(w.cap[1]) * sizeof(PairItem)));
+    w.n_items = static_cast<int*>(take(256));
+    w.counters = static_cast<unsigned*>(take(256));
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+extern "C" {
+
+int nbody_pair_min_bodies(void) { return kPairMinBodies; }
+
+size_t nbody_shard_pair_workspace_bytes(int n_slots, int slot_size) {
+    if (n_slots < 1 || slot_size < 1 || (long long)n_slots * slot_size > 0x7fffffffLL) return 0;
+    return carve_shard_pair(nullptr, n_slots, slot_size).total;
+}
+
+int nbody_shard_pair_plan_f32(int n, int n_slots, int slot_size, int my_slot, int split_phases, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+    if (!workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_plan: null pointer");
+    if (n < 1 || n_slots < 1 || slot_size < 1 || my_slot < 0 || my_slot >= n_slots ||
+        (long long)n_slots * slot_size < n || (long long)n_slots * slot_size > 0x7fffffffLL)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_plan: n %d, %d slots of %d, slot %d", n, n_slots, slot_size, my_slot);
+    if ((n_slots - 1) / 2 + 2 > kMaxPairBlocks) return fail(NBODY_ERR_UNSUPPORTED, "shard_pair_plan: %d slots", n_slots);
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    ShardPairScratch w = carve_shard_pair(workspace, n_slots, slot_size);
+    if (w.total > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "shard_pair_plan: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const ShardPairGeometry g = shard_pair_geometry(n, n_slots, slot_size, my_slot);
+    const int chunk = pair_chunk_tiles(g.units);
+    NB_CUDA(cudaMemsetAsync(w.counters, 0, kPairCounters * sizeof(unsigned), stream));
+    NB_CUDA(cudaMemsetAsync(w.n_items, 0, 2 * sizeof(int), stream));
+    if (split_phases) {
+        if (int st = launch_pair_plan(&g.own, 1, chunk, w.items[0], w.cap[0], w.n_items, stream)) return st;
+        if (g.n_cross > 0)
+            if (int st = launch_pair_plan(g.cross, g.n_cross, chunk, w.items[1], w.cap[1], w.n_items + 1, stream)) return st;
+        return NBODY_OK;
+    }
+    PairBlock all[kMaxPairBlocks];
+    all[0] = g.own;
+    for (int b = 0; b < g.n_cross; ++b) all[1 + b] = g.cross[b];
+    return launch_pair_plan(all, 1 + g.n_cross, chunk, w.items[0], w.cap[0], w.n_items, stream);
+}
+
+int nbody_shard_pair_force_f32(int phase, const float* bodies, int n_slots, int slot_size, float eps2, double* acc64,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!bodies || !acc64 || !workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_force: null pointer");
+    if (phase < 0 || phase > 1 || n_slots < 1 || slot_size < 1)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_force: phase %d, %d slots of %d", phase, n_slots, slot_size);
+    if (needs_exact_diag(eps2))
+        return fail(NBODY_ERR_UNSUPPORTED, "shard_pair_force: softening^2 = %g is below the pair path's limit", double(eps2));
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    ShardPairScratch w = carve_shard_pair(workspace, n_slots, slot_size);
+    if (w.total > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "shard_pair_force: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    PairParams pp{reinterpret_cast<const float4*>(bodies), eps2, w.items[phase], w.n_items + phase, w.counters + phase, acc64};
+    return launch_pair(pp, dev->sms, static_cast<cudaStream_t>(stream_));
+}
+
+int nbody_shard_pair_finish_f32(int integrator, const float* bodies, float* bodies_next, int i_begin, int n_local,
+                                double* acc_own, double* acc_clear, long long acc_clear_count, float* pos, float* vel,
+                                float* acc, float* vhalf, float g, float dt, float half_dt, int do_next, int n_slots,
+                                int slot_size, void* workspace, size_t workspace_bytes, void* stream_) {
+    int mode = MODE_ACCEL;
+    if (integrator != 0)
+        if (int st = mode_of(integrator, &mode)) return st;
+    if (!bodies || !acc || !acc_own || !workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_finish: null pointer");
+    if (mode != MODE_ACCEL && (!pos || !vel || !bodies_next))
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_finish: integrator needs pos, vel, bodies_next");
+    if (mode == MODE_LEAPFROG && !vhalf) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_finish: leapfrog needs vhalf");
+    if (n_local < 1 || i_begin < 0 || acc_clear_count < 0 || (acc_clear_count > 0 && !acc_clear))
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_finish: bad range");
+    const DeviceInfo* dev;
+    if (int st = current_device_info(&dev)) return st;
+    ShardPairScratch w = carve_shard_pair(workspace, n_slots, slot_size);
+    if (w.total > workspace_bytes)
+        return fail(NBODY_ERR_WORKSPACE, "shard_pair_finish: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    FinishParams fin{};
+    fin.f.bodies = reinterpret_cast<const float4*>(bodies), fin.f.bodies_next = reinterpret_cast<float4*>(bodies_next);
+    fin.f.i_begin = i_begin, fin.f.i_count = n_local, fin.f.g = g;
+    fin.f.mode = mode, fin.f.do_next = do_next, fin.f.dt = dt, fin.f.half_dt = half_dt;
+    fin.f.pos = pos, fin.f.vel = vel, fin.f.acc = acc, fin.f.vhalf = vhalf;
+    fin.acc_own = acc_own, fin.zero_extra = acc_clear, fin.zero_count = acc_clear_count;
+    fin.counters = w.counters, fin.n_counters = kPairCounters;
+    return launch_finish(fin, dev->sms, static_cast<cudaStream_t>(stream_));
 }
 
 // ------------------------------------------------------------------------------------------------ batched path

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_uint64, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_DIR, "libnbody_b200.so")
@@ -66,6 +66,15 @@ SIGNATURES = {
     "nbody_shard_energies_f32": (
         c_int,
         [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "nbody_pair_min_bodies": (c_int, []),
+    "nbody_shard_pair_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nbody_shard_pair_plan_f32": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "nbody_shard_pair_force_f32": (c_int, [c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nbody_shard_pair_finish_f32": (
+        c_int,
+        [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_float, c_float, c_float, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p],
     ),
     "nbody_batched_max_n": (c_int, []),
     "nbody_batched_integrate_f32": (
