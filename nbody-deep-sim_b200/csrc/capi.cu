@@ -99,8 +99,14 @@ class StepTimer {
         ended_ = step + 1;
         return NBODY_OK;
     }
-    // Reads every step timed so far; synchronises with the last one.
-    int finish() { return out_ ? drain(ended_) : NBODY_OK; }
+    // Reads every step timed so far, then synchronises the stream (the documented contract of passing step_ms: work
+    // queued after the last timed step, e.g. its energy evaluation, is complete when the call returns).
+    int finish() {
+        if (!out_) return NBODY_OK;
+        if (int st = drain(ended_)) return st;
+        NB_CUDA(cudaStreamSynchronize(stream_));
+        return NBODY_OK;
+    }
 
    private:
     int drain(int upto_step) {  // reads steps [read_, upto_step)

@@ -8,6 +8,14 @@ Layout: the body array (x,y,z,m float4) has world_size slots of `n_pad = ceil(n 
 global indices [r*n_pad, r*n_pad + count_r). Padding entries are massless and parked far away (1e18), so kernels may
 sweep whole slots: they contribute exactly zero.
 
+Systems of at least nbody_pair_min_bodies() bodies take the PAIR path (csrc/pair.cuh): every unordered pair of bodies
+is evaluated once over all ranks. A rank evaluates the triangle of its own slot (needs no remote data: it runs while
+the all-gather is in flight), the rectangles against the next floor((P-1)/2) slots and, for even P, half of the
+rectangle against the opposite slot; forces and reactions go to an FP64 accumulator laid out like the body array, a
+reduce-scatter (NCCL, float64, 24 B per body) hands every rank the sums of its own bodies, and a finish kernel applies
+the integrator. Per step: all-gather (16 B per body) || own triangle -> cross rectangles -> reduce-scatter -> finish.
+
+Smaller systems take the DIRECTED path below (every rank sums all j for its own i, deterministic split-j reduction).
 One step on a rank (leapfrog; Euler differs only in the epilogue), with `overlap` (default for n >= 524,288):
     all_gather(bodies_cur)  [NCCL stream]   ||   force(part 0 = own slice)  [compute stream]
     wait for the gather, force(part 1 = everything before and after the own slot, one launch over two ranges);
@@ -56,7 +64,8 @@ class ShardedSimulator:
     _integrator = None
 
     def __init__(self, *, positions, velocities, masses, g_const: float = 1.0, softening: float = 0.1,
-                 dt: float = 0.01, calc_energy: bool = False, device: str = None, group=None, overlap: bool = None):
+                 dt: float = 0.01, calc_energy: bool = False, device: str = None, group=None, overlap: bool = None,
+                 pair: bool = None):
         if device is not None and device not in ["cuda", "cpu"]:
             raise ValueError("device debe ser 'cuda', 'cpu' o None")
         self.group = group
@@ -93,6 +102,9 @@ class ShardedSimulator:
         self._parts = step_parts(self.rank, self.n_pad, self.counts, self.overlap)
         self._workspace = self._alloc_workspace()
         self.launches_per_step = len(self._parts)
+        self.pair = self._use_pair() if pair is None else bool(pair)
+        if self.pair:
+            self._setup_pair()
         # initial accelerations (simulation.py:69)
         self._prepare(0, self._bodies[0])
         self._gather(self._bodies[0]).wait()
@@ -136,6 +148,55 @@ class ShardedSimulator:
                      _ptr(self._vhalf), s["g"], s["eps2"], s["dt"], s["half_dt"], do_next, _ptr(ws), ws.numel(),
                      self._stream())
 
+    # ------------------------------------------------------------------ pair path (csrc/pair.cuh)
+
+    def _use_pair(self):
+        return self.n >= _native.lib().nbody_pair_min_bodies() and _native.f32(self.softening**2) >= 1e-16
+
+    def _setup_pair(self):
+        lib = _native.lib()
+        total = self.world_size * self.n_pad
+        self._acc64 = torch.zeros(total * 3, dtype=torch.float64, device=self.device)
+        self._acc_own = self._acc64 if self.world_size == 1 else torch.zeros(self.n_pad * 3, dtype=torch.float64,
+                                                                              device=self.device)
+        need = lib.nbody_shard_pair_workspace_bytes(self.world_size, self.n_pad)
+        self._pair_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._pair_split = bool(self.overlap and self.world_size > 1)
+        _native.call("nbody_shard_pair_plan_f32", self.n, self.world_size, self.n_pad, self.rank, int(self._pair_split),
+                     _ptr(self._pair_ws), self._pair_ws.numel(), self._stream())
+        self.launches_per_step = (2 if self._pair_split else 1) + 1  # pair launch(es) + finish
+
+    def _pair_force(self, phase, bodies):
+        _native.call("nbody_shard_pair_force_f32", phase, _ptr(bodies), self.world_size, self.n_pad,
+                     _native.f32(self.softening**2), _ptr(self._acc64), _ptr(self._pair_ws), self._pair_ws.numel(),
+                     self._stream())
+
+    def _pair_reduce(self):
+        """Every rank's accumulator holds partial sums for all slots: sum them slot by slot onto the owners."""
+        if self.world_size > 1:
+            dist.reduce_scatter_tensor(self._acc_own, self._acc64, group=self.group)
+
+    def _pair_finish(self, integrator, bodies, bodies_next, do_next):
+        s = self._scalars()
+        clear, clear_n = (self._acc64, self._acc64.numel()) if self.world_size > 1 else (None, 0)
+        _native.call("nbody_shard_pair_finish_f32", integrator, _ptr(bodies), _ptr(bodies_next), self.i_begin, self.n_local,
+                     _ptr(self._acc_own), _ptr(clear), clear_n, _ptr(self.positions), _ptr(self.velocities),
+                     _ptr(self.accelerations), _ptr(self._vhalf), s["g"], s["dt"], s["half_dt"], do_next,
+                     self.world_size, self.n_pad, _ptr(self._pair_ws), self._pair_ws.numel(), self._stream())
+
+    def _force_all_pair(self, integrator, bodies, bodies_next, do_next, gather_work):
+        if self._pair_split:
+            self._pair_force(0, bodies)  # own triangle while the gather is in flight
+            if gather_work is not None:
+                gather_work.wait()
+            self._pair_force(1, bodies)
+        else:
+            if gather_work is not None:
+                gather_work.wait()
+            self._pair_force(0, bodies)
+        self._pair_reduce()
+        self._pair_finish(integrator, bodies, bodies_next, do_next)
+
     def _local_energies(self, bodies):
         """This rank's (u, k) partial sums as a device tensor of two doubles."""
         out = torch.empty(2, dtype=torch.float64, device=self.device)
@@ -168,6 +229,9 @@ class ShardedSimulator:
     def _force_all(self, integrator, bodies, bodies_next, do_next, gather_work=None):
         """With overlap: own part while the gather is in flight, then the rest. Without: wait, then one sweep.
         The last launch runs the epilogue."""
+        if self.pair:
+            self._force_all_pair(integrator, bodies, bodies_next, do_next, gather_work)
+            return
         if len(self._parts) == 1:
             if gather_work is not None:
                 gather_work.wait()

@@ -21,7 +21,7 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol():
     lib = _native.lib()
     names = declared_symbols()
-    assert len(names) >= 21
+    assert len(names) >= 29
     for name in names:
         assert hasattr(lib, name), name
     assert sorted(_native.SIGNATURES) == names  # the binding covers exactly the header
@@ -160,5 +160,7 @@ def test_binding_argument_counts_match_the_header():
                 assert ctype is ctypes.c_float, (name, decl)
             elif "size_t" in decl:
                 assert ctype is ctypes.c_size_t, (name, decl)
+            elif "long long" in decl:
+                assert ctype is ctypes.c_longlong, (name, decl)
             else:
                 assert ctype is ctypes.c_int, (name, decl)

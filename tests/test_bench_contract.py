@@ -45,3 +45,30 @@ def test_our_arm_refuses_to_run_without_a_gpu():
         return
     r = run_bench("--steps", "1")
     assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_config4_and_config3_lines():
+    """The other workloads print the same contract line through the CPU arm (bounded samples)."""
+    r = run_bench("--impl", "reference", "--workload", "config4", "--steps", "1", "--warmup", "0", "--n-bodies", "4096",
+                  "--cpu-rows-per-step", "64")
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip())
+    assert d["config"]["workload"].startswith("config4") and d["config"]["n_bodies"] == 4096 and d["value"] > 0
+    r = run_bench("--impl", "reference", "--workload", "config3", "--steps", "1", "--warmup", "0",
+                  "--cpu-systems-per-step", "1", "--cpu-inner-steps", "3")
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip())
+    assert d["config"]["workload"].startswith("config3") and d["config"]["systems"] == 4096
+    assert d["config"]["interactions_per_step"] == 4096 * 512 * 512 * 1000 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["metric"] == "pairwise_interactions_per_second"
+
+
+def test_reference_arm_uses_every_host_thread_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use the whole host (VERDICT r1, weak #6)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--n-bodies", "4096", "--cpu-rows-per-step", "64"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip())
+    assert d["cpu_baseline"]["cores"] == os.cpu_count()

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_rows
+from conftest import assert_accelerations_agree, rel_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -137,17 +137,87 @@ def test_emulated_ranks_match_oracle_and_single_gpu(world, n, integrator, merger
 
     cls = simulation.LeapFrogSimulator if integrator == "leapfrog" else simulation.EulerSimulator
     single = cls(positions=pos, velocities=vel, masses=mass, calc_energy=False, **S01)
-    assert rel_rows(acc0, single.accelerations.cpu().numpy()).max() <= 5e-6
+    assert_accelerations_agree(acc0, single.accelerations.cpu().numpy(), pos, mass, S01["g_const"], S01["softening"])
     ref = single.run(steps)[-1]
     em.advance(steps)
     for key, want_t in (("pos", ref.positions), ("vel", ref.velocities)):
         w = want_t.numpy()
         assert np.abs(em.gathered(key) - w).max() <= 1e-6 * np.abs(w).max(), key
     acc = em.gathered("acc")
-    assert rel_rows(acc, ref.accelerations.numpy()).max() <= 5e-6
+    err = rel_rows(acc, ref.accelerations.numpy())
+    assert np.quantile(err, 0.999) <= 3e-6 and err.max() <= 1e-4, (np.quantile(err, 0.999), err.max())
     # and the final accelerations against the oracle at the final positions
     p_fin = em.gathered("pos") if integrator == "euler" else ref.positions.numpy()
     want = np.stack([c_oracle.accelerations_f64(p_fin, mass, S01["g_const"], S01["softening"], int(i), int(i) + 1)[0]
                      for i in rows])
     if integrator == "leapfrog":  # leapfrog's recorded acceleration belongs to the recorded positions
         assert rel_rows(acc[rows], want).max() <= 1e-5
+
+
+class EmulatedPairRanks(EmulatedRanks):
+    """The same emulation for the pair path (csrc/pair.cuh): every rank accumulates forces AND reactions for the part
+    of the interaction matrix it owns into its own full-size FP64 accumulator; the reduce-scatter is a sum of the
+    ranks' accumulators slot by slot; nbody_shard_pair_finish_f32 applies the integrator."""
+
+    def __init__(self, pos, vel, mass, world, integrator, split):
+        from galaxify import _native, sharded
+
+        self.split = split
+        n_pad, _ = sharded.shard_layout(len(mass), world)
+        dev = torch.device("cuda")
+        self.acc64 = [torch.zeros(world * n_pad * 3, dtype=torch.float64, device=dev) for _ in range(world)]
+        self.acc_own = [torch.zeros(n_pad * 3, dtype=torch.float64, device=dev) for _ in range(world)]
+        need = _native.lib().nbody_shard_pair_workspace_bytes(world, n_pad)
+        self.pws = [torch.empty(need, dtype=torch.uint8, device=dev) for _ in range(world)]
+        for r in range(world):
+            _native.call("nbody_shard_pair_plan_f32", len(mass), world, n_pad, r, int(split), self.pws[r].data_ptr(),
+                         self.pws[r].numel(), None)
+        super().__init__(pos, vel, mass, world, integrator, overlap=True)
+
+    def _force_all(self, integ, bodies, bodies_next, do_next):
+        p, sc = self.ptr, self.sc
+        for r in range(self.world):
+            for phase in ((0, 1) if self.split else (0,)):
+                self.nat.call("nbody_shard_pair_force_f32", phase, p(bodies), self.world, self.n_pad, sc["eps2"],
+                              p(self.acc64[r]), p(self.pws[r]), self.pws[r].numel(), None)
+        full = torch.stack(self.acc64).sum(0).view(self.world, self.n_pad * 3)  # what the reduce-scatter delivers
+        for r, st in enumerate(self.state):
+            self.acc_own[r].copy_(full[r])
+            self.nat.call("nbody_shard_pair_finish_f32", integ, p(bodies), p(bodies_next), r * self.n_pad, self.counts[r],
+                          p(self.acc_own[r]), p(self.acc64[r]), self.acc64[r].numel(), p(st["pos"]), p(st["vel"]),
+                          p(st["acc"]), p(st["vhalf"]), sc["g"], sc["dt"], sc["half_dt"], do_next, self.world, self.n_pad,
+                          p(self.pws[r]), self.pws[r].numel(), None)
+
+
+@pytest.mark.parametrize("world,n,integrator,merger,split", [
+    (1, 66000, "leapfrog", False, False), (2, 70001, "leapfrog", False, True), (2, 70001, "euler", False, False),
+    (3, 100003, "leapfrog", True, True), (4, 131072, "euler", True, True), (5, 90000, "leapfrog", False, False),
+    (8, 65541, "leapfrog", False, True), (8, 262144, "leapfrog", True, True), (6, 262144, "euler", True, False),
+    (8, 20001, "leapfrog", False, True)])
+def test_emulated_ranks_pair_path(world, n, integrator, merger, split):
+    """Every unordered pair exactly once over all ranks: own-slot triangles, cyclic rectangles, and the half
+    rectangle of even world sizes; sizes where slots are not multiples of any tile."""
+    from galaxify import _native, simulation
+    from oracle import c_oracle
+
+    pos, vel, mass = _system(n, merger)
+    code = _native.INTEGRATOR_LEAPFROG if integrator == "leapfrog" else _native.INTEGRATOR_EULER
+    steps = 3
+    em = EmulatedPairRanks(pos, vel, mass, world, code, split)
+    rows = np.unique(np.concatenate([np.arange(0, n, max(1, n // 192)), [0, n - 1, em.n_pad - 1, em.n_pad % n]]))
+    want = np.stack([c_oracle.accelerations_f64(pos, mass, S01["g_const"], S01["softening"], int(i), int(i) + 1)[0]
+                     for i in rows])
+    acc0 = em.gathered("acc")
+    assert np.isfinite(acc0).all()
+    assert rel_rows(acc0[rows], want).max() <= 1e-5
+
+    cls = simulation.LeapFrogSimulator if integrator == "leapfrog" else simulation.EulerSimulator
+    single = cls(positions=pos, velocities=vel, masses=mass, calc_energy=False, **S01)
+    assert_accelerations_agree(acc0, single.accelerations.cpu().numpy(), pos, mass, S01["g_const"], S01["softening"])
+    ref = single.run(steps)[-1]
+    em.advance(steps)
+    for key, want_t in (("pos", ref.positions), ("vel", ref.velocities)):
+        w = want_t.numpy()
+        assert np.abs(em.gathered(key) - w).max() <= 1e-6 * np.abs(w).max(), key
+    # the accumulators are left clean for the next step
+    assert all(float(a.abs().max()) == 0.0 for a in em.acc64)
