@@ -197,9 +197,10 @@ def cpu_baseline(workload, data, rows):
         pos, vel, mass = data
         n = pos.shape[1]
         cpu_sample_batched(pos, vel, mass, 1, 2)
-        probe = cpu_sample_batched(pos, vel, mass, 1, 20)
-        systems = 2
-        steps = int(min(1000, max(20, 20 * 6.0 / probe)))  # ~12 s in total
+        probe = cpu_sample_batched(pos, vel, mass, 1, 20) / 21  # seconds per force evaluation of one system
+        budget = 12.0 / probe  # force evaluations in ~12 s
+        steps = int(min(CONFIG3["inner_steps"], max(20, budget / 2)))
+        systems = int(max(1, min(len(pos), budget / (steps + 1))))
         secs = cpu_sample_batched(pos, vel, mass, systems, steps)
         # force evaluations: one per step plus the one in the constructor (simulation.py:69)
         return {"value": systems * (steps + 1) * n * n / secs, "unit": UNIT, "cores": cores, "kind": "port",
@@ -560,7 +561,7 @@ def run_batched(args, dev, rank, world):
         total_ms, secs, h2d, d2h = float(tmax[0]), float(tmax[1]), int(t[2]), int(t[3])
     inter = c["systems"] * n * n * inner
     return dict(n=n, total_ms=total_ms, kernel_ms=kernel_ms, launches=launches, clocks=clocks.summary(),
-                e2e_value=inter * args.steps / secs, h2d=h2d, d2h=d2h, cpu_data=(pos[:4], vel[:4], mass[:4]),
+                e2e_value=inter * args.steps / secs, h2d=h2d, d2h=d2h, cpu_data=(pos[:32], vel[:32], mass[:32]),
                 interactions_per_step=inter, parity=parity, kernel_interactions=n_sys * n * n * inner,
                 kernel=f"batched_kernel (one cluster per system, {inner} steps per launch), {n_sys} systems on this GPU; "
                        f"e2e records every {rec}th state ({slots} slots) and copies it to the host")

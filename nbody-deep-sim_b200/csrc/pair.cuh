@@ -14,9 +14,9 @@
 //   * symmetric items: warp w walks the 32-body blocks of the tile in the rotated order (w + round) % kWarps, one named
 //     barrier per round, so no two warps are ever on the same block. Inside a round the warp is a systolic ring: at step
 //     s lane L meets j-body (L+s)&31 (read from shared memory), accumulates the force on its own i-bodies, and adds the
-//     reaction to three scalars that move one lane per step by shuffle; after 32 steps lane L holds the reaction on
-//     j-body L from all 32*2*kPairs i-bodies of the warp and adds it (plain FP64 read-add-write, no atomics) to the
-//     tile's reaction buffer in shared memory. Per tile the buffer is flushed to the FP64 global accumulators with
+//     reaction to three scalars that move one lane per step by shuffle; after the 32 steps the lane adds them (plain
+//     FP64 read-add-write, no atomics: lanes hold distinct j-bodies) to the tile's reaction buffer in shared memory at
+//     the j-body they belong to. Per tile the buffer is flushed to the FP64 global accumulators with
 //     RED.ADD.F64; per item the i-sums (FP32 runs of 32 folded into FP64 registers, as force.cuh) go the same way.
 //   * directed items (the J-tiles inside the I-tile's own index range, i.e. the diagonal): the force.cuh loop, no
 //     reaction; the self term is d = 0 times a finite weight, exactly zero (callers route a tiny softening to
@@ -127,6 +127,12 @@ struct PairParams {
 
 constexpr int kPairStages = 4;
 constexpr int kPairLookahead = 2;
+// Steps between folds of the travelling reaction sums into FP64. 32 = once per round: FP32 runs of 32 steps x 4
+// i-bodies = 128 terms. Measured on the config4 merger (tools/diag_pair_accuracy.py, profiles/r2_pair_fold_steps.log):
+// folding every 8 / 16 steps (32- / 64-term runs) costs 7.5% / 5.5% of the kernel and does not move the error of the
+// worst-conditioned bodies (1.2e-7 / 1.4e-7 / 1.5e-7 x condition number at 8 / 16 / 32, against 1.3e-7 for force.cuh's
+// 32-term runs): at that level the rounding of the individual terms dominates, not the summation.
+constexpr int kReactFoldSteps = 32;
 
 template <int kWarps>
 struct PairRing {
@@ -162,6 +168,21 @@ struct PairRing {
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[seq % kPairStages]);
     }
 };
+
+// FP64 read-add-write of one shared-memory word, as an asm statement WITHOUT a memory clobber: the compiler keeps
+// software-pipelining the tile loads of later steps across it (a C++ store to the buffer would order them, because it
+// cannot prove that the buffer and the tile ring do not alias; measured: 7% of the kernel). Ordering against the other
+// accesses to the buffer (zeroing, flush) comes from the named barriers between them, which do clobber memory.
+__device__ __forceinline__ void smem_add_f64(uint32_t addr, double v) {
+    asm volatile(
+        "{\n"
+        ".reg .f64 t;\n"
+        "ld.shared.f64 t, [%0];\n"
+        "add.f64 t, t, %1;\n"
+        "st.shared.f64 [%0], t;\n"
+        "}\n" ::"r"(addr),
+        "d"(v));
+}
 
 // Orders generic-proxy writes to shared memory before later async-proxy (TMA) writes to the same bytes.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -251,6 +272,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) pair_kernel(const Pai
                     compute_barrier<kCT>();
                 }
                 double* rb = react + size_t(rbuf) * kTileJ * 3;
+                const uint32_t rb_s = smem_u32(rb);
                 for (int r = 0; r < kWarps; ++r) {
                     const int jblk = (warp + r) % kWarps;
                     if (jblk * 32 < count) {
@@ -282,15 +304,21 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) pair_kernel(const Pai
                                 sy = __fmaf_rn(-wj.x, dy.x, sy), sy = __fmaf_rn(-wj.y, dy.y, sy);
                                 sz = __fmaf_rn(-wj.x, dz.x, sz), sz = __fmaf_rn(-wj.y, dz.y, sz);
                             }
-                            // the j-body this lane meets next is the one lane+1 just met: fetch its reaction sums
-                            const int src = (lane + 1) & 31;
-                            sx = __shfl_sync(0xffffffffu, sx, src);
-                            sy = __shfl_sync(0xffffffffu, sy, src);
-                            sz = __shfl_sync(0xffffffffu, sz, src);
+                            if ((s & (kReactFoldSteps - 1)) == kReactFoldSteps - 1) {
+                                // every kReactFoldSteps steps the travelling FP32 sums (kReactFoldSteps * 2*kPairs
+                                // terms) are folded into the tile's FP64 buffer at the j-body they belong to; lanes
+                                // hold distinct j-bodies, so there is no conflict
+                                const uint32_t rj = rb_s + uint32_t(jblk * 32 + ((lane + s) & 31)) * 24u;
+                                smem_add_f64(rj, double(sx)), smem_add_f64(rj + 8, double(sy)), smem_add_f64(rj + 16, double(sz));
+                                sx = sy = sz = 0.f;
+                            } else {
+                                // the j-body this lane meets next is the one lane+1 just met: fetch its reaction sums
+                                const int src = (lane + 1) & 31;
+                                sx = __shfl_sync(0xffffffffu, sx, src);
+                                sy = __shfl_sync(0xffffffffu, sy, src);
+                                sz = __shfl_sync(0xffffffffu, sz, src);
+                            }
                         }
-                        // lane L now holds the reaction on j-body jblk*32 + L from all of this warp's i-bodies
-                        double* rj = rb + size_t(jblk * 32 + lane) * 3;
-                        rj[0] += double(sx), rj[1] += double(sy), rj[2] += double(sz);
                         fold();
                     }
                     compute_barrier<kCT>();  // rounds in lockstep: no two warps on one j-block

@@ -68,7 +68,10 @@ def assert_accelerations_agree(a, b, pos, mass, g_const, softening, quantile_tol
     """Two FP32 evaluations of the same accelerations by kernels with different summation orders. Almost every body
     agrees to a few 1e-7; the few whose forces nearly cancel (condition number kappa of the sum in the hundreds, close
     to a galaxy's centre) part by kappa times the rounding unit, so the worst bodies are each held to the
-    conditioning-aware bound against the FP64 oracle instead: max(1e-5, 1e-7 kappa)."""
+    conditioning-aware bound against the FP64 oracle instead: max(1e-5, 2e-7 kappa). 2e-7 ~ 3 u (u = 2^-24): every
+    FP32 term m_j d / r^3 carries about three roundings, whatever the summation does afterwards; measured on the
+    config4 merger: 1.3e-7 kappa for the directed kernel, 1.2-1.5e-7 kappa for the pair kernel
+    (tools/diag_pair_accuracy.py)."""
     from oracle import c_oracle
 
     err = rel_rows(a, b)
@@ -78,4 +81,4 @@ def assert_accelerations_agree(a, b, pos, mass, g_const, softening, quantile_tol
     want, kappa = c_oracle.accelerations_cond_f64(pos, mass, g_const, softening, worst)
     for got in (a, b):
         e = rel_rows(np.asarray(got)[worst], want)
-        assert np.all(e <= np.maximum(1e-5, 1e-7 * kappa)), (e.max(), kappa.max())
+        assert np.all(e <= np.maximum(1e-5, 2e-7 * kappa)), (e.max(), (e / kappa).max())
