@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -241,10 +242,12 @@ constexpr int kPairTileJ = kPairWarps * 32;                   // 384
 constexpr int kPairMinBodies = 65536;
 constexpr int kPairCounters = 4;
 
-// J-tiles per symmetric item: about 48 items per SM, so that the tail of the dynamic schedule (one item) stays ~2%,
-// but items long enough to amortise their prologue (i-body load, pipeline refill, i-sum flush).
+// J-tiles per symmetric item. An item costs ~3 us of prologue (two CTA barriers, i-body load, first tile's latency) and
+// the dynamic schedule ends with about half an item of idle time per SM, so for items of t us in a launch of T us per
+// SM the loss is 3/t + t/(2T), least at t = sqrt(6 T). One (I-tile, J-tile) unit takes ~56 us on one SM, hence
+// chunk = sqrt(units) / 37 (26 tiles at N = 1M, 6 at 262,144, 2 for one of 8 ranks at 262,144).
 int pair_chunk_tiles(long long sym_tile_units) {
-    long long c = sym_tile_units / (kPlanSms * 48LL);
+    long long c = (long long)(std::sqrt(double(sym_tile_units)) / 37.0 + 0.5);
     if (c < 1) c = 1;
     if (c > 32) c = 32;
     return int(c);

@@ -13,7 +13,8 @@ is evaluated once over all ranks. A rank evaluates the triangle of its own slot 
 the all-gather is in flight), the rectangles against the next floor((P-1)/2) slots and, for even P, half of the
 rectangle against the opposite slot; forces and reactions go to an FP64 accumulator laid out like the body array, a
 reduce-scatter (NCCL, float64, 24 B per body) hands every rank the sums of its own bodies, and a finish kernel applies
-the integrator. Per step: all-gather (16 B per body) || own triangle -> cross rectangles -> reduce-scatter -> finish.
+the integrator. Per step: all-gather (16 B per body) -> one persistent pair launch -> reduce-scatter -> finish; with
+overlap=True the own-slot triangle is a launch of its own that starts before the gather is waited for.
 
 Smaller systems take the DIRECTED path below (every rank sums all j for its own i, deterministic split-j reduction).
 One step on a rank (leapfrog; Euler differs only in the epilogue), with `overlap` (default for n >= 524,288):
@@ -98,6 +99,7 @@ class ShardedSimulator:
             b[self.i_begin + self.n_local : self.i_begin + self.n_pad, :3] = 1e18  # whole array can divide by zero
         # Overlapping the gather with the own-slice force costs one more launch per step: worth it only when a step
         # is long compared to a launch (the gather itself is tens of microseconds either way).
+        self._overlap_requested = overlap
         self.overlap = (self.n >= 524288) if overlap is None else bool(overlap)
         self._parts = step_parts(self.rank, self.n_pad, self.counts, self.overlap)
         self._workspace = self._alloc_workspace()
@@ -161,7 +163,11 @@ class ShardedSimulator:
                                                                               device=self.device)
         need = lib.nbody_shard_pair_workspace_bytes(self.world_size, self.n_pad)
         self._pair_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        self._pair_split = bool(self.overlap and self.world_size > 1)
+        # Splitting the own-slot triangle off (to run it while the all-gather is in flight) is opt-in: the persistent
+        # pair kernel fills every SM, so the NCCL kernel only gets to run in the first launch's tail anyway, and the
+        # second launch adds a second tail; measured on 2 GPUs at N = 1M the gather is 0.16 ms of a 179 ms step
+        # (tools/diag_sharded_pair.py, profiles/r2_diag_sharded_pair.log).
+        self._pair_split = bool(self._overlap_requested is True and self.world_size > 1)
         _native.call("nbody_shard_pair_plan_f32", self.n, self.world_size, self.n_pad, self.rank, int(self._pair_split),
                      _ptr(self._pair_ws), self._pair_ws.numel(), self._stream())
         self.launches_per_step = (2 if self._pair_split else 1) + 1  # pair launch(es) + finish
