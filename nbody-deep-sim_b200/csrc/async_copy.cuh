@@ -127,4 +127,46 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return y;
 }
 
+// Packed FP32 pairs as opaque 64-bit registers. The CUDA float2 intrinsics (__ffma2_rn, ...) split a pair into two
+// 32-bit values and re-pack them (mov.b64) at every use, and ptxas does not always keep loop-invariant pairs in an
+// aligned register pair: the pair kernel's systolic loop carried 9 MOVs per step for that. A value of this type IS the
+// register pair, so nothing has to be re-packed.
+using f32x2 = unsigned long long;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) {
+    float lo;
+    asm("{ .reg .f32 t; mov.b64 {%0, t}, %1; }" : "=f"(lo) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float hi2(f32x2 v) {
+    float hi;
+    asm("{ .reg .f32 t; mov.b64 {t, %0}, %1; }" : "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 }  // namespace nb

@@ -37,51 +37,46 @@ struct BatchedParams {
 
 constexpr int kBatchedFold = 32;  // FP32 accumulation run length, as in force.cuh
 
+// The state of a thread's bodies is held as packed pairs (two bodies per 64-bit register, one register per component)
+// for the whole kernel: the j loop then uses them as they are. With scalar state the pairs were re-packed by two MOVs at
+// every use inside the loop (2.8 MOVs per j on top of 12 FMA-pipe instructions, profiles/r2_sass_batched.txt).
 template <int kPairs, bool kExactDiag>
 __device__ __forceinline__ void batched_force(const float4* __restrict__ bodies, int n, float eps2s,
-                                              const float (&x)[2 * kPairs][3], const int (&idx)[2 * kPairs],
-                                              float (&sum)[2 * kPairs][3]) {
-    float2 nx[kPairs], ny[kPairs], nz[kPairs], ax[kPairs], ay[kPairs], az[kPairs];
+                                              const f32x2 (&x)[kPairs][3], const int (&idx)[2 * kPairs],
+                                              f32x2 (&sum)[kPairs][3]) {
+    f32x2 ax[kPairs], ay[kPairs], az[kPairs];
     double tot[2 * kPairs][3];
 #pragma unroll
-    for (int q = 0; q < kPairs; ++q) {
-        nx[q] = make_float2(-x[2 * q][0], -x[2 * q + 1][0]);
-        ny[q] = make_float2(-x[2 * q][1], -x[2 * q + 1][1]);
-        nz[q] = make_float2(-x[2 * q][2], -x[2 * q + 1][2]);
-    }
-#pragma unroll
     for (int k = 0; k < 2 * kPairs; ++k) tot[k][0] = tot[k][1] = tot[k][2] = 0.0;
-    const float2 eps2 = make_float2(eps2s, eps2s);
+    const f32x2 eps2 = pack2(eps2s, eps2s);
 
     auto interact = [&](int j) {
         const float4 b = bodies[j];
-        const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
-        const float2 bm = make_float2(b.w, b.w);
+        const f32x2 bx = pack2(b.x, b.x), by = pack2(b.y, b.y), bz = pack2(b.z, b.z), bm = pack2(b.w, b.w);
 #pragma unroll
         for (int q = 0; q < kPairs; ++q) {
-            const float2 dx = __fadd2_rn(bx, nx[q]);
-            const float2 dy = __fadd2_rn(by, ny[q]);
-            const float2 dz = __fadd2_rn(bz, nz[q]);
-            float2 r2 = __ffma2_rn(dz, dz, eps2);
-            r2 = __ffma2_rn(dy, dy, r2);
-            r2 = __ffma2_rn(dx, dx, r2);
-            float2 ri = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+            const f32x2 dx = sub2(bx, x[q][0]);
+            const f32x2 dy = sub2(by, x[q][1]);
+            const f32x2 dz = sub2(bz, x[q][2]);
+            f32x2 r2 = fma2(dz, dz, eps2);
+            r2 = fma2(dy, dy, r2);
+            r2 = fma2(dx, dx, r2);
+            float r0 = rsqrt_approx(lo2(r2)), r1 = rsqrt_approx(hi2(r2));
             if (kExactDiag) {
-                if (j == idx[2 * q]) ri.x = 0.f;
-                if (j == idx[2 * q + 1]) ri.y = 0.f;
+                if (j == idx[2 * q]) r0 = 0.f;
+                if (j == idx[2 * q + 1]) r1 = 0.f;
             }
-            const float2 ri2 = __fmul2_rn(ri, ri);
-            const float2 mri = __fmul2_rn(ri, bm);
-            const float2 w = __fmul2_rn(ri2, mri);
-            ax[q] = __ffma2_rn(w, dx, ax[q]);
-            ay[q] = __ffma2_rn(w, dy, ay[q]);
-            az[q] = __ffma2_rn(w, dz, az[q]);
+            const f32x2 ri = pack2(r0, r1);
+            const f32x2 w = mul2(mul2(ri, ri), mul2(ri, bm));
+            ax[q] = fma2(w, dx, ax[q]);
+            ay[q] = fma2(w, dy, ay[q]);
+            az[q] = fma2(w, dz, az[q]);
         }
     };
 
     for (int jb = 0; jb < n; jb += kBatchedFold) {
 #pragma unroll
-        for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
+        for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = 0ull;
         if (jb + kBatchedFold <= n) {
 #pragma unroll
             for (int u = 0; u < kBatchedFold; ++u) interact(jb + u);
@@ -90,14 +85,15 @@ __device__ __forceinline__ void batched_force(const float4* __restrict__ bodies,
         }
 #pragma unroll
         for (int q = 0; q < kPairs; ++q) {
-            tot[2 * q][0] += double(ax[q].x), tot[2 * q][1] += double(ay[q].x), tot[2 * q][2] += double(az[q].x);
-            tot[2 * q + 1][0] += double(ax[q].y), tot[2 * q + 1][1] += double(ay[q].y), tot[2 * q + 1][2] += double(az[q].y);
+            tot[2 * q][0] += double(lo2(ax[q])), tot[2 * q][1] += double(lo2(ay[q])), tot[2 * q][2] += double(lo2(az[q]));
+            tot[2 * q + 1][0] += double(hi2(ax[q])), tot[2 * q + 1][1] += double(hi2(ay[q]));
+            tot[2 * q + 1][2] += double(hi2(az[q]));
         }
     }
 #pragma unroll
-    for (int k = 0; k < 2 * kPairs; ++k)
+    for (int q = 0; q < kPairs; ++q)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sum[k][c] = float(tot[k][c]);
+        for (int c = 0; c < 3; ++c) sum[q][c] = pack2(float(tot[2 * q][c]), float(tot[2 * q + 1][c]));
 }
 
 // One thread-block CLUSTER per system: the system's i-bodies are split evenly over the cluster's CTAs (so that the
@@ -133,20 +129,24 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
 
     int idx[kI];
     bool valid[kI];
-    float x[kI][3], v[kI][3], a[kI][3], m[kI], sum[kI][3];
+    float m[kI];
+    f32x2 x[kPairs][3], v[kPairs][3], a[kPairs][3], sum[kPairs][3];  // (body 2q, body 2q+1) per component
 #pragma unroll
     for (int k = 0; k < kI; ++k) {
         const int i = i_lo + k * kBatchedThreads + tid;
         valid[k] = i < i_hi;
         idx[k] = min(i, p.n - 1);
         m[k] = mass[idx[k]];
+    }
+#pragma unroll
+    for (int q = 0; q < kPairs; ++q)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            x[k][c] = gpos[3 * idx[k] + c];
-            v[k][c] = gvel[3 * idx[k] + c];
-            a[k][c] = (p.mode == MODE_LEAPFROG) ? gacc[3 * idx[k] + c] : 0.f;
+            const int i0 = 3 * idx[2 * q] + c, i1 = 3 * idx[2 * q + 1] + c;
+            x[q][c] = pack2(gpos[i0], gpos[i1]);
+            v[q][c] = pack2(gvel[i0], gvel[i1]);
+            a[q][c] = (p.mode == MODE_LEAPFROG) ? pack2(gacc[i0], gacc[i1]) : 0ull;
         }
-    }
     // Every CTA of the cluster must be running before any of them writes into a peer's shared memory (publish()),
     // and a peer's initial load of buf0 must have finished before it is read: a cluster-wide barrier does both.
     if (csize > 1)
@@ -156,13 +156,21 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
 
     float4* cur = buf0;
     float4* nxt = buf1;
+    auto comp = [&](const f32x2 (&arr)[kPairs][3], int k, int c) { return (k & 1) ? hi2(arr[k >> 1][c]) : lo2(arr[k >> 1][c]); };
+    auto store_state = [&](float* base, const f32x2 (&arr)[kPairs][3]) {
+#pragma unroll
+        for (int k = 0; k < kI; ++k)
+            if (valid[k]) store3(base, idx[k], comp(arr, k, 0), comp(arr, k, 1), comp(arr, k, 2));
+    };
+    const f32x2 g2 = pack2(p.g, p.g), dt2 = pack2(p.dt, p.dt), h2 = pack2(p.half_dt, p.half_dt);
 
     if (p.mode == MODE_ACCEL) {
         batched_force<kPairs, kExactDiag>(cur, p.n, p.eps2, x, idx, sum);
 #pragma unroll
-        for (int k = 0; k < kI; ++k)
-            if (valid[k])
-                store3(gacc, idx[k], __fmul_rn(p.g, sum[k][0]), __fmul_rn(p.g, sum[k][1]), __fmul_rn(p.g, sum[k][2]));
+        for (int q = 0; q < kPairs; ++q)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) a[q][c] = mul2(g2, sum[q][c]);
+        store_state(gacc, a);
         return;
     }
 
@@ -171,42 +179,44 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
 #pragma unroll
         for (int k = 0; k < kI; ++k) {
             if (!valid[k]) continue;
-            const float4 b = make_float4(x[k][0], x[k][1], x[k][2], m[k]);
+            const float4 b = make_float4(comp(x, k, 0), comp(x, k, 1), comp(x, k, 2), m[k]);
             for (int r = 0; r < csize; ++r) cluster.map_shared_rank(dst, r)[idx[k]] = b;
         }
     };
 
+    // Each update is a rounded multiply followed by a rounded add (mul.rn / add.rn per lane), never an FMA, as torch
+    // evaluates `v += c * a` (simulation.py:164-170, 183-187).
     const size_t plane = size_t(p.n_systems) * p.n * 3;
     for (int s = 0; s < p.steps; ++s) {
         if (p.mode == MODE_LEAPFROG) {
             // half-kick + drift (simulation.py:164-166), publish the drifted bodies, then force + closing half-kick
 #pragma unroll
-            for (int k = 0; k < kI; ++k)
+            for (int q = 0; q < kPairs; ++q)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    v[k][c] = __fadd_rn(v[k][c], __fmul_rn(p.half_dt, a[k][c]));
-                    x[k][c] = __fadd_rn(x[k][c], __fmul_rn(p.dt, v[k][c]));
+                    v[q][c] = add2(v[q][c], mul2(h2, a[q][c]));
+                    x[q][c] = add2(x[q][c], mul2(dt2, v[q][c]));
                 }
             publish(nxt);
             cluster.sync();
             batched_force<kPairs, kExactDiag>(nxt, p.n, p.eps2, x, idx, sum);
 #pragma unroll
-            for (int k = 0; k < kI; ++k)
+            for (int q = 0; q < kPairs; ++q)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    a[k][c] = __fmul_rn(p.g, sum[k][c]);
-                    v[k][c] = __fadd_rn(v[k][c], __fmul_rn(p.half_dt, a[k][c]));
+                    a[q][c] = mul2(g2, sum[q][c]);
+                    v[q][c] = add2(v[q][c], mul2(h2, a[q][c]));
                 }
         } else {
             // force at the current positions, then v += dt*a ; x += dt*v (simulation.py:183-187)
             batched_force<kPairs, kExactDiag>(cur, p.n, p.eps2, x, idx, sum);
 #pragma unroll
-            for (int k = 0; k < kI; ++k)
+            for (int q = 0; q < kPairs; ++q)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    a[k][c] = __fmul_rn(p.g, sum[k][c]);
-                    v[k][c] = __fadd_rn(v[k][c], __fmul_rn(p.dt, a[k][c]));
-                    x[k][c] = __fadd_rn(x[k][c], __fmul_rn(p.dt, v[k][c]));
+                    a[q][c] = mul2(g2, sum[q][c]);
+                    v[q][c] = add2(v[q][c], mul2(dt2, a[q][c]));
+                    x[q][c] = add2(x[q][c], mul2(dt2, v[q][c]));
                 }
             publish(nxt);
             cluster.sync();
@@ -217,22 +227,14 @@ __global__ void __launch_bounds__(kBatchedThreads) batched_kernel(const BatchedP
 
         if (p.traj && (s + 1) % p.record_every == 0) {
             float* slot = p.traj + size_t((s + 1) / p.record_every - 1) * 3 * plane + base3;
-#pragma unroll
-            for (int k = 0; k < kI; ++k)
-                if (valid[k]) {
-                    store3(slot, idx[k], x[k][0], x[k][1], x[k][2]);
-                    store3(slot + plane, idx[k], v[k][0], v[k][1], v[k][2]);
-                    store3(slot + 2 * plane, idx[k], a[k][0], a[k][1], a[k][2]);
-                }
+            store_state(slot, x);
+            store_state(slot + plane, v);
+            store_state(slot + 2 * plane, a);
         }
     }
-#pragma unroll
-    for (int k = 0; k < kI; ++k)
-        if (valid[k]) {
-            store3(gpos, idx[k], x[k][0], x[k][1], x[k][2]);
-            store3(gvel, idx[k], v[k][0], v[k][1], v[k][2]);
-            store3(gacc, idx[k], a[k][0], a[k][1], a[k][2]);
-        }
+    store_state(gpos, x);
+    store_state(gvel, v);
+    store_state(gacc, a);
     cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 

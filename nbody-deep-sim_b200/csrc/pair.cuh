@@ -184,6 +184,13 @@ __device__ __forceinline__ void smem_add_f64(uint32_t addr, double v) {
         "d"(v));
 }
 
+// One 32-bit read-only global load that the compiler may not merge with its neighbours into a vector load.
+__device__ __forceinline__ float ldg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // Orders generic-proxy writes to shared memory before later async-proxy (TMA) writes to the same bytes.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -203,7 +210,6 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) pair_kernel(const Pai
     __syncthreads();
 
     const int n_items = *p.n_items;
-    const float2 eps2 = make_float2(p.eps2, p.eps2);
     unsigned seq_issue = 0, seq_use = 0;  // producer / consumer running tile numbers (same sequence)
     unsigned rbuf = 0;
 
@@ -220,37 +226,43 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) pair_kernel(const Pai
                 ring.issue(seq_issue++, p.bodies + item.j_begin + t * kTileJ, min(kTileJ, item.j_count - t * kTileJ));
 
         // this thread's i-bodies; slots past the end of the tile are massless copies of the first body
-        float2 nx[kPairs], ny[kPairs], nz[kPairs], mi[kPairs];
+        f32x2 nx[kPairs], ny[kPairs], nz[kPairs], mi[kPairs];
         bool valid[kI];
         {
-            float4 me[kI];
+            // Component-wise scalar loads on purpose: after a float4 load ptxas keeps the quad registers as the home of
+            // the coordinates and re-packs (x_i0, x_i1) with two MOVs at EVERY use inside the systolic loop (9 MOVs
+            // per step, profiles/r2_sass_pair_kernel.txt); loading each component into its own register lets the two
+            // halves of a pair be allocated next to each other once.
+            float cx[kI], cy[kI], cz[kI], cm[kI];
 #pragma unroll
             for (int k = 0; k < kI; ++k) {
                 const int li = k * kCT + tid;
                 valid[k] = li < item.i_count;
-                me[k] = p.bodies[item.i_begin + (valid[k] ? li : 0)];
-                if (!valid[k]) me[k].w = 0.f;
+                const float* src = reinterpret_cast<const float*>(p.bodies + item.i_begin + (valid[k] ? li : 0));
+                cx[k] = ldg_f32(src), cy[k] = ldg_f32(src + 1), cz[k] = ldg_f32(src + 2), cm[k] = ldg_f32(src + 3);
+                if (!valid[k]) cm[k] = 0.f;
             }
 #pragma unroll
             for (int q = 0; q < kPairs; ++q) {
-                nx[q] = make_float2(-me[2 * q].x, -me[2 * q + 1].x);
-                ny[q] = make_float2(-me[2 * q].y, -me[2 * q + 1].y);
-                nz[q] = make_float2(-me[2 * q].z, -me[2 * q + 1].z);
-                mi[q] = make_float2(me[2 * q].w, me[2 * q + 1].w);
+                nx[q] = pack2(-cx[2 * q], -cx[2 * q + 1]);
+                ny[q] = pack2(-cy[2 * q], -cy[2 * q + 1]);
+                nz[q] = pack2(-cz[2 * q], -cz[2 * q + 1]);
+                mi[q] = pack2(cm[2 * q], cm[2 * q + 1]);
             }
         }
         double tot[kI][3];
 #pragma unroll
         for (int k = 0; k < kI; ++k) tot[k][0] = tot[k][1] = tot[k][2] = 0.0;
-        float2 ax[kPairs], ay[kPairs], az[kPairs];
+        f32x2 ax[kPairs], ay[kPairs], az[kPairs];
         auto fold = [&]() {
 #pragma unroll
             for (int q = 0; q < kPairs; ++q) {
-                tot[2 * q][0] += double(ax[q].x), tot[2 * q][1] += double(ay[q].x), tot[2 * q][2] += double(az[q].x);
-                tot[2 * q + 1][0] += double(ax[q].y), tot[2 * q + 1][1] += double(ay[q].y);
-                tot[2 * q + 1][2] += double(az[q].y);
+                tot[2 * q][0] += double(lo2(ax[q])), tot[2 * q][1] += double(lo2(ay[q])), tot[2 * q][2] += double(lo2(az[q]));
+                tot[2 * q + 1][0] += double(hi2(ax[q])), tot[2 * q + 1][1] += double(hi2(ay[q]));
+                tot[2 * q + 1][2] += double(hi2(az[q]));
             }
         };
+        const f32x2 eps2 = pack2(p.eps2, p.eps2);
 
         for (int t = 0; t < ntiles; ++t) {
             if (tid == 0 && t + kPairLookahead < ntiles)
@@ -278,31 +290,31 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) pair_kernel(const Pai
                     if (jblk * 32 < count) {
                         const float4* __restrict__ blk = tj + jblk * 32;
 #pragma unroll
-                        for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
+                        for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = 0ull;
                         float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
                         for (int s = 0; s < 32; ++s) {
                             const float4 b = blk[(lane + s) & 31];
-                            const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
-                            const float2 bm = make_float2(b.w, b.w);
+                            const f32x2 bx = pack2(b.x, b.x), by = pack2(b.y, b.y), bz = pack2(b.z, b.z), bm = pack2(b.w, b.w);
 #pragma unroll
                             for (int q = 0; q < kPairs; ++q) {
-                                const float2 dx = __fadd2_rn(bx, nx[q]);
-                                const float2 dy = __fadd2_rn(by, ny[q]);
-                                const float2 dz = __fadd2_rn(bz, nz[q]);
-                                float2 r2 = __ffma2_rn(dz, dz, eps2);
-                                r2 = __ffma2_rn(dy, dy, r2);
-                                r2 = __ffma2_rn(dx, dx, r2);
-                                const float2 ri = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-                                const float2 ri3 = __fmul2_rn(__fmul2_rn(ri, ri), ri);
-                                const float2 wi = __fmul2_rn(ri3, bm);     // weight of j's pull on the two i-bodies
-                                const float2 wj = __fmul2_rn(ri3, mi[q]);  // weight of their pull on j
-                                ax[q] = __ffma2_rn(wi, dx, ax[q]);
-                                ay[q] = __ffma2_rn(wi, dy, ay[q]);
-                                az[q] = __ffma2_rn(wi, dz, az[q]);
-                                sx = __fmaf_rn(-wj.x, dx.x, sx), sx = __fmaf_rn(-wj.y, dx.y, sx);
-                                sy = __fmaf_rn(-wj.x, dy.x, sy), sy = __fmaf_rn(-wj.y, dy.y, sy);
-                                sz = __fmaf_rn(-wj.x, dz.x, sz), sz = __fmaf_rn(-wj.y, dz.y, sz);
+                                const f32x2 dx = add2(bx, nx[q]);
+                                const f32x2 dy = add2(by, ny[q]);
+                                const f32x2 dz = add2(bz, nz[q]);
+                                f32x2 r2 = fma2(dz, dz, eps2);
+                                r2 = fma2(dy, dy, r2);
+                                r2 = fma2(dx, dx, r2);
+                                const f32x2 ri = pack2(rsqrt_approx(lo2(r2)), rsqrt_approx(hi2(r2)));
+                                const f32x2 ri3 = mul2(mul2(ri, ri), ri);
+                                const f32x2 wi = mul2(ri3, bm);     // weight of j's pull on the two i-bodies
+                                const f32x2 wj = mul2(ri3, mi[q]);  // weight of their pull on j
+                                ax[q] = fma2(wi, dx, ax[q]);
+                                ay[q] = fma2(wi, dy, ay[q]);
+                                az[q] = fma2(wi, dz, az[q]);
+                                const float wj0 = lo2(wj), wj1 = hi2(wj);
+                                sx = __fmaf_rn(-wj0, lo2(dx), sx), sx = __fmaf_rn(-wj1, hi2(dx), sx);
+                                sy = __fmaf_rn(-wj0, lo2(dy), sy), sy = __fmaf_rn(-wj1, hi2(dy), sy);
+                                sz = __fmaf_rn(-wj0, lo2(dz), sz), sz = __fmaf_rn(-wj1, hi2(dz), sz);
                             }
                             if ((s & (kReactFoldSteps - 1)) == kReactFoldSteps - 1) {
                                 // every kReactFoldSteps steps the travelling FP32 sums (kReactFoldSteps * 2*kPairs
@@ -335,24 +347,23 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) pair_kernel(const Pai
             } else {
                 for (int jb = 0; jb < count; jb += 32) {
 #pragma unroll
-                    for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
+                    for (int q = 0; q < kPairs; ++q) ax[q] = ay[q] = az[q] = 0ull;
                     auto interact = [&](int jj) {
                         const float4 b = tj[jj];
-                        const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
-                        const float2 bm = make_float2(b.w, b.w);
+                        const f32x2 bx = pack2(b.x, b.x), by = pack2(b.y, b.y), bz = pack2(b.z, b.z), bm = pack2(b.w, b.w);
 #pragma unroll
                         for (int q = 0; q < kPairs; ++q) {
-                            const float2 dx = __fadd2_rn(bx, nx[q]);
-                            const float2 dy = __fadd2_rn(by, ny[q]);
-                            const float2 dz = __fadd2_rn(bz, nz[q]);
-                            float2 r2 = __ffma2_rn(dz, dz, eps2);
-                            r2 = __ffma2_rn(dy, dy, r2);
-                            r2 = __ffma2_rn(dx, dx, r2);
-                            const float2 ri = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-                            const float2 w = __fmul2_rn(__fmul2_rn(ri, ri), __fmul2_rn(ri, bm));
-                            ax[q] = __ffma2_rn(w, dx, ax[q]);
-                            ay[q] = __ffma2_rn(w, dy, ay[q]);
-                            az[q] = __ffma2_rn(w, dz, az[q]);
+                            const f32x2 dx = add2(bx, nx[q]);
+                            const f32x2 dy = add2(by, ny[q]);
+                            const f32x2 dz = add2(bz, nz[q]);
+                            f32x2 r2 = fma2(dz, dz, eps2);
+                            r2 = fma2(dy, dy, r2);
+                            r2 = fma2(dx, dx, r2);
+                            const f32x2 ri = pack2(rsqrt_approx(lo2(r2)), rsqrt_approx(hi2(r2)));
+                            const f32x2 w = mul2(mul2(ri, ri), mul2(ri, bm));
+                            ax[q] = fma2(w, dx, ax[q]);
+                            ay[q] = fma2(w, dy, ay[q]);
+                            az[q] = fma2(w, dz, az[q]);
                         }
                     };
                     if (jb + 32 <= count) {

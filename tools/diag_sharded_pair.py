@@ -60,7 +60,21 @@ for s in range(steps):
     tot += t0.elapsed_time(t5)
     cur ^= 1
     dist.barrier()
+# free-running loops (no host sync between steps), with and without the bench's L2 flush
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+free = {}
+for name, cb in (("free", None), ("free+flush", lambda s_, b_: flush.zero_())):
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    a = ev()
+    sim._advance(20, on_state=cb)
+    c = ev()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(c) / 20], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    free[name] = float(t.item())
 line = f"rank {rank} n {n} split {sim._pair_split}: " + "  ".join(f"{k} {acc[k] / steps:8.3f} ms" for k in names)
-print(line + f"   total {tot / steps:8.3f} ms", flush=True)
+print(line + f"   total {tot / steps:8.3f} ms   " + "  ".join(f"{k} {v:.3f} ms/step" for k, v in free.items()), flush=True)
 dist.barrier()
 dist.destroy_process_group()
