@@ -127,6 +127,13 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return y;
 }
 
+// One 32-bit read-only global load that the compiler may not merge with its neighbours into a vector load.
+__device__ __forceinline__ float ldg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // Packed FP32 pairs as opaque 64-bit registers. The CUDA float2 intrinsics (__ffma2_rn, ...) split a pair into two
 // 32-bit values and re-pack them (mov.b64) at every use, and ptxas does not always keep loop-invariant pairs in an
 // aligned register pair: the pair kernel's systolic loop carried 9 MOVs per step for that. A value of this type IS the

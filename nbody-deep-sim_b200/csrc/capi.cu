@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -883,6 +884,9 @@ static int batched_launch(int mode, float* pos, float* vel, float* acc, const fl
     p.g = g, p.eps2 = eps2, p.dt = dt, p.half_dt = half_dt;
     p.mass = mass, p.pos = pos, p.vel = vel, p.acc = acc, p.traj = traj, p.n_systems = n_systems;
     const bool exact = needs_exact_diag(eps2);
+    // Shapes re-tuned on the packed-state kernel (profiles/r2_batched_shapes.log): at 512 bodies a cluster of two
+    // 128-thread CTAs wins when there are few systems per SM (0.615 vs 0.57 for one 256-thread CTA at 512 systems); with
+    // thousands of systems one CTA per system is 2% ahead (0.678 vs 0.661), not enough to add a second code path.
     if (n <= 64) return batched_launch_shape<1, 32>(p, 1, exact, stream);
     if (n <= 128) return batched_launch_shape<1, 64>(p, 1, exact, stream);
     if (n <= 256) return batched_launch_shape<1, 128>(p, 1, exact, stream);

@@ -7,8 +7,12 @@
 // The pair sum is evaluated as -G * sum_i m_i * phi_i with phi_i = sum_{j > i} m_j / (|r_ij| + eps) (the upper
 // triangle, as simulation.py:113), on the same TMA-fed j-tile ring as the force kernel; j tiles that lie entirely
 // below a CTA's i-bodies are skipped, so only half of the N^2 pairs are evaluated.
-// Per interaction: 3 FADD2 + 3 FMUL2/FFMA2 (r^2) + MUFU.SQRT + FADD2 + MUFU.RCP + FFMA2, so this kernel is MUFU-bound
-// (2 MUFU per interaction), and it is kept apart from the force kernel for that reason. Pairs with j <= i are masked by index (the reference masks the diagonal with +inf and
+// 1/(|r| + eps) needs |r| = sqrt(r^2) AND a reciprocal: two MUFU operations per interaction where the force needs one,
+// which is why this kernel is kept apart from the force kernel. With both on the XU pipe (MUFU.SQRT + MUFU.RCP) the
+// kernel sat at 92% of the XU pipe's throughput (round 1: 255 ms at N = 1M). Now |r| = r^2 * rsqrt(r^2) (one MUFU),
+// and of the two bodies packed in a register pair one takes MUFU.RCP and the other a Newton reciprocal on the FMA pipe
+// (rcp_newton), which balances the two pipes: per pair of interactions 3 MUFU (24 XU cycles) and 9 packed + 6 scalar
+// FMA-pipe instructions (24 cycles). Pairs with j <= i are masked by index (the reference masks the diagonal with +inf and
 // keeps triu(1), simulation.py:107-113); distinct coincident bodies contribute m_i m_j / eps exactly as there.
 // Sums over runs of 32 bodies are FP32, everything across runs / tiles / threads / CTAs is FP64, and every cross-CTA sum is taken in a
 // fixed order, so the result is deterministic and closer to the exact value than the reference's FP32 reduction.
@@ -40,6 +44,18 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// 1/x for a positive normal x without the MUFU unit: the integer seed (magic constant minus the bit pattern, within
+// 12.5% of 1/x) refined by two cubically convergent steps s <- s + s*(e + e*e), e = 1 - x*s: 0.125 -> 2e-3 -> 8e-9
+// relative, i.e. correct to FP32 rounding. Six FMA-pipe operations and one integer subtraction.
+__device__ __forceinline__ float rcp_newton(float x) {
+    float s = __int_as_float(0x7EF311C7 - __float_as_int(x));
+    float e = __fmaf_rn(-x, s, 1.f);
+    s = __fmaf_rn(s, __fmaf_rn(e, e, e), s);
+    e = __fmaf_rn(-x, s, 1.f);
+    s = __fmaf_rn(s, __fmaf_rn(e, e, e), s);
+    return s;
+}
+
 template <int kBlock>
 __device__ __forceinline__ double block_sum(double v, double* scratch /* kBlock/32 doubles */) {
 #pragma unroll
@@ -51,6 +67,13 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /* kBlock/
         for (int w = 0; w < kBlock / 32; ++w) total += scratch[w];
     return total;  // valid on thread 0
 }
+
+struct MaskOn {
+    static constexpr bool value = true;
+};
+struct MaskOff {
+    static constexpr bool value = false;
+};
 
 template <int kPairs, int kWarps, int kMinBlocks, int kTileJ>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(const EnergyParams p) {
@@ -102,6 +125,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
 #pragma unroll
     for (int k = 0; k < kI; ++k) phi[k] = 0.0;
     const float2 eps = make_float2(p.eps, p.eps);
+    const float2 tiny = make_float2(1e-30f, 1e-30f);
 
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + kEnergyLookahead < ntiles) ring.issue(t + kEnergyLookahead);
@@ -110,7 +134,11 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
         const float4* __restrict__ tj = ring.tile(t);
         float2 acc[kPairs];
         ring.wait(t);
-        auto interact = [&](int jj) {
+        // Only tiles that reach down to this CTA's own i-bodies need the j > i mask; for every tile above them (all but
+        // a handful) the mask-free variant saves three integer compares and selects per (i-pair, j), which matters:
+        // with the reciprocal split over two pipes the loop is bound by instruction issue, not by a pipe.
+        const bool masked = jt <= p.i_begin + tile_base + kTileI - 1;
+        auto interact = [&](int jj, auto use_mask) {
             const float4 b = tj[jj];
             const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
             const float2 bm = make_float2(b.w, b.w);
@@ -120,13 +148,19 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
                 const float2 dx = __fadd2_rn(bx, nx[q]);
                 const float2 dy = __fadd2_rn(by, ny[q]);
                 const float2 dz = __fadd2_rn(bz, nz[q]);
-                float2 r2 = __fmul2_rn(dx, dx);
+                float2 r2 = __ffma2_rn(dx, dx, tiny);  // + 1e-30: |r| = r2 * rsqrt(r2) stays finite for coincident bodies
                 r2 = __ffma2_rn(dy, dy, r2);
                 r2 = __ffma2_rn(dz, dz, r2);
-                const float2 d = __fadd2_rn(make_float2(sqrt_approx(r2.x), sqrt_approx(r2.y)), eps);
-                float2 inv = make_float2(rcp_approx(d.x), rcp_approx(d.y));
-                if (jg <= gi[2 * q]) inv.x = 0.f;
-                if (jg <= gi[2 * q + 1]) inv.y = 0.f;
+                // |r| = r2 * rsqrt(r2): one MUFU per body; then 1/(|r| + eps) by MUFU.RCP for one body of the pair and
+                // by two cubic Newton steps on the FMA pipe for the other, so that the XU and FMA pipes carry equal
+                // loads (3 MUFU and 24 FMA-pipe cycles per pair of interactions, against 4 MUFU = 32 XU cycles before)
+                const float2 ry = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+                const float2 d = __fadd2_rn(__fmul2_rn(r2, ry), eps);
+                float2 inv = make_float2(rcp_approx(d.x), rcp_newton(d.y));
+                if (decltype(use_mask)::value) {
+                    if (jg <= gi[2 * q]) inv.x = 0.f;
+                    if (jg <= gi[2 * q + 1]) inv.y = 0.f;
+                }
                 acc[q] = __ffma2_rn(bm, inv, acc[q]);
             }
         };
@@ -134,11 +168,14 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) potential_kernel(cons
         for (int jb = 0; jb < count; jb += kEnergyFold) {
 #pragma unroll
             for (int q = 0; q < kPairs; ++q) acc[q] = make_float2(0.f, 0.f);
-            if (jb + kEnergyFold <= count) {
+            if (jb + kEnergyFold <= count && !masked) {
 #pragma unroll 8
-                for (int u = 0; u < kEnergyFold; ++u) interact(jb + u);
+                for (int u = 0; u < kEnergyFold; ++u) interact(jb + u, MaskOff{});
+            } else if (jb + kEnergyFold <= count) {
+#pragma unroll 4
+                for (int u = 0; u < kEnergyFold; ++u) interact(jb + u, MaskOn{});
             } else {
-                for (int jj = jb; jj < count; ++jj) interact(jj);
+                for (int jj = jb; jj < count; ++jj) interact(jj, MaskOn{});
             }
 #pragma unroll
             for (int q = 0; q < kPairs; ++q) {

@@ -184,13 +184,6 @@ __device__ __forceinline__ void smem_add_f64(uint32_t addr, double v) {
         "d"(v));
 }
 
-// One 32-bit read-only global load that the compiler may not merge with its neighbours into a vector load.
-__device__ __forceinline__ float ldg_f32(const float* p) {
-    float v;
-    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
 // Orders generic-proxy writes to shared memory before later async-proxy (TMA) writes to the same bytes.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

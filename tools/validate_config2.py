@@ -34,7 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=10000)
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_config2_validation.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_config2_validation.json"))
     args = ap.parse_args()
     kw = dict(g_const=4.5e-6, softening=0.05, dt=1e-4)
     pos, vel, mass = galaxies.generate_disk(n_bodies=args.n, total_mass=1.0, radial_scale=3.0, height_scale=0.3,
