@@ -252,35 +252,41 @@ def reference_config1_block(dev_index):
     return out
 
 
-def reference_gpu_block(n=16384):
+def reference_gpu_block(sizes=(1024, 4096, 16384)):
     """BASELINE.md 3 'reference GPU' line: the reference's own operators (simulation.py:80-88, restated in
     oracle/galaxify_oracle.accelerations) run unfused by torch on this GPU, synchronised, next to this engine."""
     from galaxify import galaxies, simulation
     from oracle import galaxify_oracle as oracle
 
-    pos, vel, mass = galaxies.generate_disk(n_bodies=n, seed=7, **GAL)
-    p = torch.tensor(pos, dtype=torch.float32, device="cuda")
-    m = torch.tensor(mass, dtype=torch.float32, device="cuda")
-    oracle.accelerations(p, m, S01["g_const"], S01["softening"], chunk=n, device="cuda")
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
+    rows = []
+    for n in sizes:
+        pos, vel, mass = galaxies.generate_disk(n_bodies=n, seed=7, **GAL)
+        p = torch.tensor(pos, dtype=torch.float32, device="cuda")
+        m = torch.tensor(mass, dtype=torch.float32, device="cuda")
         oracle.accelerations(p, m, S01["g_const"], S01["softening"], chunk=n, device="cuda")
-    torch.cuda.synchronize()
-    ref_ms = (time.perf_counter() - t0) / reps * 1e3
-    sim = simulation.LeapFrogSimulator(positions=pos, velocities=vel, masses=mass, calc_energy=False, **S01)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sim.compute_accelerations()
-    e0.record()
-    for _ in range(20):
+        torch.cuda.synchronize()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            oracle.accelerations(p, m, S01["g_const"], S01["softening"], chunk=n, device="cuda")
+        torch.cuda.synchronize()
+        ref_ms = (time.perf_counter() - t0) / reps * 1e3
+        del p, m
+        torch.cuda.empty_cache()
+        sim = simulation.LeapFrogSimulator(positions=pos, velocities=vel, masses=mass, calc_energy=False, **S01)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sim.compute_accelerations()
-    e1.record()
-    torch.cuda.synchronize()
-    ours_ms = e0.elapsed_time(e1) / 20
-    return {"n_bodies": n, "reference_ops_cuda_ms": ref_ms, "reference_ops_cuda_interactions_per_s": n * n / ref_ms * 1e3,
-            "ours_ms": ours_ms, "ours_interactions_per_s": n * n / ours_ms * 1e3,
-            "note": "one compute_accelerations; reference operators = torch ATen on the same B200, unchunked (N,N,3) temporaries"}
+        e0.record()
+        for _ in range(20):
+            sim.compute_accelerations()
+        e1.record()
+        torch.cuda.synchronize()
+        ours_ms = e0.elapsed_time(e1) / 20
+        rows.append({"n_bodies": n, "reference_ops_cuda_ms": ref_ms,
+                     "reference_ops_cuda_interactions_per_s": n * n / ref_ms * 1e3, "ours_ms": ours_ms,
+                     "ours_interactions_per_s": n * n / ours_ms * 1e3})
+    return {"sizes": rows, "note": "one compute_accelerations; reference operators = torch ATen on the same B200, "
+                                   "unchunked (N,N,3) temporaries, wall clock with synchronize; ours = CUDA events"}
 
 
 def run_reference_arm(args, rank, json_out):

@@ -153,7 +153,9 @@ class BaseSimulator:
                 _native.call("nbody_traj_energies_f32", _ptr(traj), _ptr(self.masses), steps // record_every, 1,
                              self.n, s["g"], s["eps"], _ptr(energies), self._stream())
         if step_ms is not None:
-            end.synchronize()
+            # like nbody_integrate_f32 with step_ms: everything queued by this call (the energies too) is complete
+            # when it returns, which is what run() relies on before it stages the chunk on its copy stream
+            torch.cuda.current_stream().synchronize()
             step_ms[:] = start.elapsed_time(end) / max(steps, 1)
 
     def _integrate(self, steps, record_every, traj, energies, step_ms):
