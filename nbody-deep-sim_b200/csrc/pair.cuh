@@ -305,9 +305,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) pair_kernel(const Pai
                                 ay[q] = fma2(wi, dy, ay[q]);
                                 az[q] = fma2(wi, dz, az[q]);
                                 const float wj0 = lo2(wj), wj1 = hi2(wj);
-                                sx = __fmaf_rn(-wj0, lo2(dx), sx), sx = __fmaf_rn(-wj1, hi2(dx), sx);
-                                sy = __fmaf_rn(-wj0, lo2(dy), sy), sy = __fmaf_rn(-wj1, hi2(dy), sy);
-                                sz = __fmaf_rn(-wj0, lo2(dz), sz), sz = __fmaf_rn(-wj1, hi2(dz), sz);
+                                // grouped by weight: three consecutive FFMAs share one multiplicand (operand reuse)
+                                sx = __fmaf_rn(-wj0, lo2(dx), sx), sy = __fmaf_rn(-wj0, lo2(dy), sy), sz = __fmaf_rn(-wj0, lo2(dz), sz);
+                                sx = __fmaf_rn(-wj1, hi2(dx), sx), sy = __fmaf_rn(-wj1, hi2(dy), sy), sz = __fmaf_rn(-wj1, hi2(dz), sz);
                             }
                             if ((s & (kReactFoldSteps - 1)) == kReactFoldSteps - 1) {
                                 // every kReactFoldSteps steps the travelling FP32 sums (kReactFoldSteps * 2*kPairs
