@@ -344,14 +344,18 @@ def run_reference_arm(args, rank, json_out):
 CLOCK_WARMUP_SECONDS = 1.0
 
 
-def clock_warmup_steps(warmup_seconds, warmup_steps):
+def clock_warmup_steps(probe_seconds, probe_steps):
     """Extra untimed steps so that the GPU has been under load for about CLOCK_WARMUP_SECONDS when the timed region
     starts. The W warm-up steps of the contract are too short for that when a step takes a few milliseconds (config4 on
     8 GPUs: 3 steps = 10 ms after seconds of host-side initial-condition generation with the GPU idle), and the first
     ~50 ms after idle run below the boost clock: the same 20 steps measured 4.8 ms/step right after 3 warm-up steps and
-    3.1 ms/step once warm (profiles/r2_diag_sharded_pair.log)."""
-    per_step = max(warmup_seconds / max(warmup_steps, 1), 1e-5)
-    return int(min(5000, max(0, (CLOCK_WARMUP_SECONDS - warmup_seconds) / per_step)))
+    3.1 ms/step once warm (profiles/r2_diag_sharded_pair.log). `probe_seconds` is the wall time of `probe_steps` steps
+    run AFTER the W warm-up steps (whose own wall time includes one-off costs such as NCCL communicator set-up)."""
+    per_step = max(probe_seconds / max(probe_steps, 1), 1e-5)
+    return int(min(5000, max(0, CLOCK_WARMUP_SECONDS / per_step)))
+
+
+CLOCK_PROBE_STEPS = 3
 
 
 def fp32_peak_tflops(device_index):
@@ -398,11 +402,14 @@ def run_single(args, dev):
         if record:
             kernel_ms.append(float(ms[0]))
 
-    t0 = time.perf_counter()
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
-    for _ in range(clock_warmup_steps(time.perf_counter() - t0, args.warmup)):
+    t0 = time.perf_counter()
+    for _ in range(CLOCK_PROBE_STEPS):
+        step(False)
+    torch.cuda.synchronize()
+    for _ in range(clock_warmup_steps(time.perf_counter() - t0, CLOCK_PROBE_STEPS)):
         step(False)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -448,10 +455,12 @@ def run_sharded(args, dev, rank, world):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
     # warm-up = the timed code path (both ping-pong body arrays go through a collective at least once)
-    t0 = time.perf_counter()
     sim._advance(args.warmup, on_state=lambda s, bodies: flush.zero_())
     torch.cuda.synchronize()
-    extra = torch.tensor([clock_warmup_steps(time.perf_counter() - t0, args.warmup)], device="cuda")
+    t0 = time.perf_counter()
+    sim._advance(CLOCK_PROBE_STEPS, on_state=lambda s, bodies: flush.zero_())
+    torch.cuda.synchronize()
+    extra = torch.tensor([clock_warmup_steps(time.perf_counter() - t0, CLOCK_PROBE_STEPS)], device="cuda")
     dist.all_reduce(extra, op=dist.ReduceOp.MAX)  # every rank must run the same number of collective steps
     sim._advance(int(extra.item()), on_state=lambda s, bodies: flush.zero_())
     torch.cuda.synchronize()
@@ -528,11 +537,13 @@ def run_batched(args, dev, rank, world):
         if record:
             kernel_ms.append((a, b))
 
-    t0 = time.perf_counter()
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
-    for _ in range(clock_warmup_steps(time.perf_counter() - t0, args.warmup)):
+    t0 = time.perf_counter()
+    step(False)
+    torch.cuda.synchronize()
+    for _ in range(clock_warmup_steps(time.perf_counter() - t0, 1)):
         step(False)
     torch.cuda.synchronize()
     if world > 1:
