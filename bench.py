@@ -131,6 +131,10 @@ class ClockSampler:
             except Exception:
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # The first call of each query is slow (tens of ms) and stalls kernel launches of this process while it
+            # runs: make it here, right after the warm-up steps and before the timed region opens.
+            self.pre_mhz = pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
         except Exception as e:  # NVML missing: report it, do not fake numbers
             self.nv, self.err = None, repr(e)
         self.t = threading.Thread(target=self._loop, daemon=True)
@@ -138,6 +142,7 @@ class ClockSampler:
             self.t = None
 
     def _loop(self):
+        self._stop.wait(min(self.period, 0.02))  # let the first launches of the timed region go out undisturbed
         while not self._stop.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
@@ -158,8 +163,11 @@ class ClockSampler:
             self.t.join()
 
     def summary(self):
-        if not self.nv or not self.samples:
+        if not self.nv:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        if not self.samples:  # timed region shorter than the first sampling delay
+            return {"sm_mhz": self.pre_mhz, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0,
+                    "note": "no sample fell inside the timed region; sm_mhz was read right before it, under warm-up load"}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
 
