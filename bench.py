@@ -108,68 +108,85 @@ def workload_config(workload, n, gpus):
 # --------------------------------------------------------------------------------------------------- clocks
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU with NVML from a background thread.
+
+    start() is called BEFORE the warm-up steps, so that the expensive first calls of the NVML queries (tens of ms, during
+    which this process's kernel launches stall) are paid outside the timed region; `with sampler:` then marks the timed
+    region, and only samples taken inside it are reported. One sample per 0.2 s, on rank 0 only: on an 8-GPU box every
+    poll costs the polled process milliseconds of launch latency (measured: 8 ranks polling at 10 Hz added 1.1 ms to every
+    step, rank 0 alone at 10 Hz still 0.3 ms)."""
 
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.1, enabled=True):
-        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+    def __init__(self, index, period=0.2, enabled=True):
+        self.samples, self.max_mhz, self._stop = [], None, threading.Event()  # samples: (time, mhz, reason mask)
         self.period = float(os.environ.get("NBODY_BENCH_CLOCK_PERIOD", period))
-        if not enabled:  # ranks other than 0: eight processes polling NVML at once stall each other's kernel launches
-            self.nv, self.err = None, "sampling is done by rank 0 only"  # (measured: +1.1 ms per step on 8 GPUs)
+        self.t0 = self.t1 = None
+        self.nv, self.t = None, None
+        if not enabled:
+            self.err = "sampling is done by rank 0 only"
             return
         try:
             import pynvml
 
             pynvml.nvmlInit()
-            self.nv = pynvml
             try:  # CUDA_VISIBLE_DEVICES can renumber devices: match NVML to the CUDA device by UUID
                 uuid = str(torch.cuda.get_device_properties(index).uuid)
                 self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
             except Exception:
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            # The first call of each query is slow (tens of ms) and stalls kernel launches of this process while it
-            # runs: make it here, right after the warm-up steps and before the timed region opens.
-            self.pre_mhz = pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            self.nv = pynvml
         except Exception as e:  # NVML missing: report it, do not fake numbers
-            self.nv, self.err = None, repr(e)
-        self.t = threading.Thread(target=self._loop, daemon=True)
-        if not self.nv:
-            self.t = None
+            self.err = repr(e)
+
+    def start(self):
+        if self.nv and self.t is None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+        return self
 
     def _loop(self):
-        self._stop.wait(min(self.period, 0.02))  # let the first launches of the timed region go out undisturbed
         while not self._stop.is_set():
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                self.reasons.update(name for bit, name in self.REASONS.items() if mask & bit and bit != 0x1)
+                self.samples.append((time.perf_counter(), mhz, mask))
             except Exception:
                 pass
             self._stop.wait(self.period)
 
     def __enter__(self):
-        if self.nv:
-            self.t.start()
+        self.start()
+        self.t0 = time.perf_counter()
         return self
 
     def __exit__(self, *a):
+        self.t1 = time.perf_counter()
         self._stop.set()
-        if self.nv:
+        if self.t is not None:
             self.t.join()
 
     def summary(self):
         if not self.nv:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
-        if not self.samples:  # timed region shorter than the first sampling delay
-            return {"sm_mhz": self.pre_mhz, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0,
-                    "note": "no sample fell inside the timed region; sm_mhz was read right before it, under warm-up load"}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        inside = [x for x in self.samples if self.t0 <= x[0] <= self.t1]
+        note = None
+        if not inside:  # region shorter than the sampling period: the last sample before it (GPU under warm-up load)
+            inside = [x for x in self.samples if x[0] <= self.t0][-1:]
+            note = "no sample fell inside the timed region; the last one before it (under warm-up load) is reported"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no samples"}
+        reasons = set()
+        for _, _, mask in inside:
+            reasons.update(name for bit, name in self.REASONS.items() if mask & bit and bit != 0x1)
+        out = {"sm_mhz": statistics.median(x[1] for x in inside), "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+               "samples": len(inside), "period_s": self.period}
+        if note:
+            out["note"] = note
+        return out
 
 
 # --------------------------------------------------------------------------------------------------- CPU arms
@@ -410,6 +427,7 @@ def run_single(args, dev):
         if record:
             kernel_ms.append(float(ms[0]))
 
+    clocks = ClockSampler(dev).start()
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
@@ -422,7 +440,7 @@ def run_single(args, dev):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _native.launch_count()
-    with ClockSampler(dev) as clocks:
+    with clocks:
         e0.record()
         for _ in range(args.steps):
             step(True)
@@ -463,6 +481,7 @@ def run_sharded(args, dev, rank, world):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
     # warm-up = the timed code path (both ping-pong body arrays go through a collective at least once)
+    clocks = ClockSampler(dev, enabled=(rank == 0)).start()
     sim._advance(args.warmup, on_state=lambda s, bodies: flush.zero_())
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -476,7 +495,7 @@ def run_sharded(args, dev, rank, world):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _native.launch_count()
-    with ClockSampler(dev, enabled=(rank == 0)) as clocks:
+    with clocks:
         e0.record()
         # K consecutive steps of one run: each step's epilogue opens the next, L2 flushed between steps
         sim._advance(args.steps, on_state=lambda s, bodies: flush.zero_())
@@ -545,6 +564,7 @@ def run_batched(args, dev, rank, world):
         if record:
             kernel_ms.append((a, b))
 
+    clocks = ClockSampler(dev, enabled=(rank == 0)).start()
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
@@ -561,7 +581,7 @@ def run_batched(args, dev, rank, world):
         torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _native.launch_count()
-    with ClockSampler(dev, enabled=(rank == 0)) as clocks:
+    with clocks:
         e0.record()
         for _ in range(args.steps):
             step(True)
