@@ -150,6 +150,12 @@ int nbody_shard_energies_f32(const float* bodies, const float* vel, int n_total,
  * (item lists, counters) must be preserved between plan, force and finish. No reference counterpart. */
 int nbody_pair_min_bodies(void);
 size_t nbody_shard_pair_workspace_bytes(int n_slots, int slot_size);
+/* The part of the interaction matrix rank `my_slot` evaluates, as up to `max_blocks` blocks of 5 ints
+ * (i_lo, i_hi, j_lo, j_hi, triangle) in global body indices: block 0 is the triangle of the own slot (unordered pairs
+ * within [i_lo, i_hi)), the others are rectangles (every i in [i_lo, i_hi) with every j in [j_lo, j_hi)). Over all ranks
+ * the blocks cover every unordered pair of the n bodies exactly once. Pure host function (no device needed); returns the
+ * number of blocks or a negative NBODY_ERR_* code. */
+int nbody_shard_pair_blocks(int n, int n_slots, int slot_size, int my_slot, int* blocks, int max_blocks);
 int nbody_shard_pair_plan_f32(int n, int n_slots, int slot_size, int my_slot, int split_phases, void* workspace,
                               size_t workspace_bytes, void* stream);
 int nbody_shard_pair_force_f32(int phase, const float* bodies, int n_slots, int slot_size, float eps2, double* acc64,

@@ -769,6 +769,23 @@ size_t nbody_shard_pair_workspace_bytes(int n_slots, int slot_size) {
     return carve_shard_pair(nullptr, n_slots, slot_size).total;
 }
 
+int nbody_shard_pair_blocks(int n, int n_slots, int slot_size, int my_slot, int* blocks, int max_blocks) {
+    if (!blocks) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_blocks: null pointer");
+    if (n < 1 || n_slots < 1 || slot_size < 1 || my_slot < 0 || my_slot >= n_slots ||
+        (long long)n_slots * slot_size < n || (long long)n_slots * slot_size > 0x7fffffffLL)
+        return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_blocks: n %d, %d slots of %d, slot %d", n, n_slots, slot_size, my_slot);
+    if ((n_slots - 1) / 2 + 2 > kMaxPairBlocks) return fail(NBODY_ERR_UNSUPPORTED, "shard_pair_blocks: %d slots", n_slots);
+    const ShardPairGeometry g = shard_pair_geometry(n, n_slots, slot_size, my_slot);
+    if (1 + g.n_cross > max_blocks) return fail(NBODY_ERR_WORKSPACE, "shard_pair_blocks: %d blocks > %d", 1 + g.n_cross, max_blocks);
+    auto put = [&](int k, const PairBlock& b) {
+        blocks[5 * k + 0] = b.i_lo, blocks[5 * k + 1] = b.i_hi, blocks[5 * k + 2] = b.j_lo, blocks[5 * k + 3] = b.j_hi;
+        blocks[5 * k + 4] = b.triangle;
+    };
+    put(0, g.own);
+    for (int b = 0; b < g.n_cross; ++b) put(1 + b, g.cross[b]);
+    return 1 + g.n_cross;
+}
+
 int nbody_shard_pair_plan_f32(int n, int n_slots, int slot_size, int my_slot, int split_phases, void* workspace,
                               size_t workspace_bytes, void* stream_) {
     if (!workspace) return fail(NBODY_ERR_INVALID_ARGUMENT, "shard_pair_plan: null pointer");

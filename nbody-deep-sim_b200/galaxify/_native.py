@@ -69,6 +69,7 @@ SIGNATURES = {
     ),
     "nbody_pair_min_bodies": (c_int, []),
     "nbody_shard_pair_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nbody_shard_pair_blocks": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), c_int]),
     "nbody_shard_pair_plan_f32": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "nbody_shard_pair_force_f32": (c_int, [c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nbody_shard_pair_finish_f32": (

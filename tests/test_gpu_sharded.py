@@ -77,14 +77,16 @@ def _check(tmp_path, world, n, integrator, steps, overlap=None):
 
 
 @pytest.mark.parametrize("integrator", ["leapfrog", "euler"])
-@pytest.mark.parametrize("n", [1000, 20001])
+@pytest.mark.parametrize("n", [1000, 20001, 70001])
 def test_sharded_world1_equals_single_gpu(tmp_path, n, integrator):
+    """n = 70,001 takes the pair path (plan / force / finish through ShardedSimulator, no collective at world 1)."""
     _check(tmp_path, 1, n, integrator, 4)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("integrator,n,overlap", [("leapfrog", 20001, True), ("leapfrog", 20001, False),
                                                   ("euler", 4097, True), ("euler", 4096, False),
-                                                  ("leapfrog", 262144, True), ("leapfrog", 262144, None)])
+                                                  ("leapfrog", 262144, True), ("leapfrog", 262144, None),
+                                                  ("euler", 70001, None)])
 def test_sharded_world2_equals_single_gpu(tmp_path, integrator, n, overlap):
     _check(tmp_path, 2, n, integrator, 3, overlap)
