@@ -440,7 +440,7 @@ int mode_of(int integrator, int* mode) {
 
 extern "C" {
 
-int nbody_version(void) { return 100; }
+int nbody_version(void) { return 101; }  // 1.1: pair path, rollout integrator, momentum (additions only)
 
 const char* nbody_status_string(int status) {
     switch (status) {

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_status_strings():
     lib = _native.lib()
-    assert lib.nbody_version() == 100
+    assert lib.nbody_version() == 101
     assert lib.nbody_status_string(0) == b"ok"
     for code in (-1, -2, -3, -4, -5):
         assert lib.nbody_status_string(code) not in (b"ok", b"unknown status")
