@@ -234,26 +234,49 @@ struct Workspace {
     size_t total;
 };
 
-// Pair kernel shape (tools/tune_pair.cu, profiles/r2_tune_pair.log): 384 threads x 4 i-bodies, 1 CTA/SM.
-constexpr int kPairPairs = 2, kPairWarps = 12, kPairMinBlocks = 1;
-constexpr int kPairTileI = kPairWarps * 32 * 2 * kPairPairs;  // 1536
-constexpr int kPairTileJ = kPairWarps * 32;                   // 384
-// Systems at least this large take the pair path (below it there are too few (I-tile, J-tile) units to balance
-// 148 persistent CTAs, and force.cuh's deterministic split-j reduction is kept).
-constexpr int kPairMinBodies = 65536;
+// Pair kernel shape (tools/tune_pair.cu, profiles/r2_tune_pair.log): 128 threads x 6 i-bodies, 2 CTAs/SM, I-tiles of 768
+// and J-tiles of 128 bodies. Small CTAs win: the per-round barrier spans 4 warps instead of 12, two CTAs per SM cover
+// each other's barriers and item prologues, and small tiles leave less to quantisation (0.935 of the FP32 peak at
+// N = 1M against 0.883 for 384 threads x 4 i-bodies; 0.82 at N = 32,768, where the 384-thread shape got 0.62).
+constexpr int kPairPairs = 3, kPairWarps = 4, kPairMinBlocks = 2;
+constexpr int kPairTileI = kPairWarps * 32 * 2 * kPairPairs;  // 768
+constexpr int kPairTileJ = kPairWarps * 32;                   // 128
+// Systems at least this large take the pair path: at 32,768 bodies it runs a force evaluation in 0.35 ms against
+// 0.455 ms for force.cuh; at 16,384 the two are level (0.11 vs 0.125 ms plus the finish launch) and force.cuh's
+// deterministic split-j reduction is kept.
+constexpr int kPairMinBodies = 32768;
 constexpr int kPairCounters = 4;
 
-// J-tiles per symmetric item. An item costs ~3 us of prologue (two CTA barriers, i-body load, first tile's latency) and
-// the dynamic schedule ends with about half an item of idle time per SM, so for items of t us in a launch of T us per
-// SM the loss is 3/t + t/(2T), least at t = sqrt(6 T). One (I-tile, J-tile) unit takes ~56 us on one SM, hence
-// chunk = sqrt(units) / 37 (26 tiles at N = 1M, 6 at 262,144, 2 for one of 8 ranks at 262,144).
+// J-tiles per symmetric item. An item costs a few microseconds of prologue (two CTA barriers, i-body load, first tile's
+// latency) and the dynamic schedule ends with about half an item of idle time per CTA slot, so for items of t us in a
+// launch of T us per slot the loss is ~3/t + t/(2T), least at t = sqrt(6 T). One (I-tile, J-tile) unit takes ~19 us on
+// one of the 296 CTA slots, hence chunk = sqrt(units) / 30; measured flat between half and twice that
+// (profiles/r2_tune_pair.log), capped at 64 tiles.
 int pair_chunk_tiles(long long sym_tile_units) {
-    long long c = (long long)(std::sqrt(double(sym_tile_units)) / 37.0 + 0.5);
+    long long c = (long long)(std::sqrt(double(sym_tile_units)) / 30.0 + 0.5);
     if (c < 1) c = 1;
-    if (c > 32) c = 32;
+    if (c > 64) c = 64;
     return int(c);
 }
 long long tiles_of(long long bodies, int tile) { return (bodies + tile - 1) / tile; }
+// Exact number of items pair_plan_kernel writes for a block list (same arithmetic, on the host).
+long long pair_items_exact(const PairBlock* blocks, int n_blocks, int chunk_tiles) {
+    const long long chunk = (long long)chunk_tiles * kPairTileJ;
+    long long items = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        const PairBlock& blk = blocks[b];
+        const long long i_tiles = tiles_of(blk.i_hi - blk.i_lo, kPairTileI);
+        for (long long a = 0; a < i_tiles; ++a) {
+            const long long i_begin = blk.i_lo + a * kPairTileI;
+            long long s_lo = blk.triangle ? i_begin + kPairTileI : blk.j_lo;
+            if (s_lo > blk.j_hi) s_lo = blk.j_hi;
+            const long long len = blk.j_hi - s_lo;
+            items += len / chunk + (len % chunk ? 1 : 0) + (blk.triangle ? 1 : 0);
+        }
+    }
+    return items;
+}
+
 // Upper bound of the item count of one block with i_len x j_len bodies.
 long long pair_block_items(long long i_len, long long j_len, int chunk_tiles) {
     return tiles_of(i_len, kPairTileI) * (tiles_of(j_len, kPairTileJ) / chunk_tiles + 3);
@@ -377,6 +400,9 @@ bool use_pair(int n_total, float eps2) { return n_total >= kPairMinBodies && !ne
 int launch_pair_plan(const PairBlock* blocks, int n_blocks, int chunk_tiles, PairItem* items, int max_items, int* n_items,
                      cudaStream_t stream) {
     if (n_blocks < 1 || n_blocks > kMaxPairBlocks) return fail(NBODY_ERR_INVALID_ARGUMENT, "pair plan: %d blocks", n_blocks);
+    const long long need = pair_items_exact(blocks, n_blocks, chunk_tiles);
+    if (need > max_items)  // never silently drop items: the sums would be short
+        return fail(NBODY_ERR_WORKSPACE, "pair plan: %lld items exceed the list's capacity of %d", need, max_items);
     PairPlanParams pp{};
     for (int b = 0; b < n_blocks; ++b) pp.blocks[b] = blocks[b];
     pp.n_blocks = n_blocks, pp.tile_i = kPairTileI, pp.tile_j = kPairTileJ, pp.chunk_tiles = chunk_tiles;
@@ -746,9 +772,14 @@ ShardPairScratch carve_shard_pair(void* base, int n_slots, int slot_size) {
         off += align_up(bytes, 256);
         return p;
     };
-    // capacities for the smallest chunk (1 tile): a bound for every chunk size the planner may pick
-    const long long own = pair_block_items(slot_size, slot_size, 1);
-    const long long cross = pair_block_items(slot_size, slot_size, 1) * ((n_slots - 1) / 2 + 1);
+    // Capacities for a chunk size no larger than any the planner can pick for this layout: n is more than
+    // (n_slots - 1) / n_slots of the padded total, so the rank's units are more than a quarter of the full-layout units
+    // and its chunk (a square root) at least half the full-layout chunk. launch_pair_plan checks the exact count.
+    const ShardPairGeometry full = shard_pair_geometry(n_slots * slot_size, n_slots, slot_size, 0);
+    int chunk_lb = pair_chunk_tiles(full.units) / 2 - 1;
+    if (chunk_lb < 1) chunk_lb = 1;
+    const long long own = pair_block_items(slot_size, slot_size, chunk_lb);
+    const long long cross = pair_block_items(slot_size, slot_size, chunk_lb) * ((n_slots - 1) / 2 + 1);
     w.cap[0] = int(own + cross);  // phase 0 holds everything when the step is not split
     w.cap[1] = int(cross);
     w.items[0] = static_cast<PairItem*>(take(size_t(w.cap[0]) * sizeof(PairItem)));

@@ -278,6 +278,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) pair_kernel(const Pai
                 }
                 double* rb = react + size_t(rbuf) * kTileJ * 3;
                 const uint32_t rb_s = smem_u32(rb);
+                // one copy of the (fully unrolled, ~35 KB) round body: unrolling the rounds as well put 190 KB of code in
+                // the kernel, more than the instruction cache holds, and cost 4.5%
+#pragma unroll 1
                 for (int r = 0; r < kWarps; ++r) {
                     const int jblk = (warp + r) % kWarps;
                     if (jblk * 32 < count) {

@@ -81,7 +81,12 @@ pair_kernel(const float4* __restrict__ bodies, int n, float eps2s, const Item* _
         float2 nx[kPairs], ny[kPairs], nz[kPairs], mi[kPairs];
         int gi[kI];
 #pragma unroll
-        for (int k = 0; k < kI; ++k) { gi[k] = item.i_tile * kTileI + k * kCT + tid; me[k] = bodies[min(gi[k], n - 1)]; if (gi[k] >= n) me[k].w = 0.f; }
+        for (int k = 0; k < kI; ++k) {  // component-wise scalar loads: see csrc/pair.cuh (no per-use MOV re-packing)
+            gi[k] = item.i_tile * kTileI + k * kCT + tid;
+            const float* src = reinterpret_cast<const float*>(bodies + min(gi[k], n - 1));
+            me[k] = make_float4(ldg_f32(src), ldg_f32(src + 1), ldg_f32(src + 2), ldg_f32(src + 3));
+            if (gi[k] >= n) me[k].w = 0.f;
+        }
 #pragma unroll
         for (int q = 0; q < kPairs; ++q) {
             nx[q] = make_float2(-me[2*q].x, -me[2*q+1].x); ny[q] = make_float2(-me[2*q].y, -me[2*q+1].y);
@@ -266,16 +271,16 @@ int main(int argc, char** argv) {
     h[0] = make_float4(0.f, 0.f, 0.f, 0.01f);
     float4* d; CK(cudaMalloc(&d, 16 * size_t(n))); CK(cudaMemcpy(d, h.data(), 16 * size_t(n), cudaMemcpyHostToDevice));
 #define RUN(P, W, B, C) run<P, W, B>("<p" #P ",w" #W ",b" #B ">", d, h, n, eps2, sms, C)
-    const int c1 = n >= (1 << 20) ? 32 : 8;
-    RUN(2, 12, 1, c1);
-    RUN(2, 12, 1, c1 / 2);
-    RUN(2, 12, 1, c1 / 4);
-    RUN(2, 10, 1, c1);
-    RUN(2, 14, 1, c1);
-    RUN(3, 10, 1, c1);
-    RUN(3, 8, 1, c1);
-    RUN(2, 8, 2, c1);
-    RUN(2, 6, 2, c1);
-    RUN(2, 6, 3, c1);
+    const int c1 = n >= (1 << 20) ? 64 : n >= 262144 ? 20 : n >= 65536 ? 5 : 2;
+    RUN(3, 4, 2, c1);
+    RUN(3, 4, 2, c1 / 2 > 0 ? c1 / 2 : 1);
+    RUN(3, 4, 2, c1 * 2);
+    RUN(2, 4, 3, c1);
+    RUN(2, 4, 3, c1 * 2);
+    RUN(2, 4, 4, c1);
+    RUN(3, 2, 4, c1 * 2);
+    RUN(3, 2, 5, c1 * 2);
+    RUN(4, 4, 2, c1);
+    RUN(4, 2, 4, c1 * 2);
     return 0;
 }
