@@ -21,7 +21,7 @@
 //   * directed items (the J-tiles inside the I-tile's own index range, i.e. the diagonal): the force.cuh loop, no
 //     reaction; the self term is d = 0 times a finite weight, exactly zero (callers route a tiny softening to
 //     force.cuh's index-masked variant instead).
-// Items are pulled from a global counter by persistent CTAs (one per SM), largest first, so there is no wave
+// Items are pulled from a global counter by persistent CTAs (kMinBlocks per SM), largest first, so there is no wave
 // quantisation: the tail is at most one item.
 //
 // Accumulation order across items is the order the RED.ADD.F64 operations land, which is not fixed: results are

@@ -1,5 +1,5 @@
-"""The Newton's-third-law ("pair") kernel path, taken for N >= 65,536 (csrc/pair.cuh): ragged sizes around its tile
-sizes (I-tiles of 1,536, J-tiles of 384, 32-body systolic blocks), both integrators, against the FP64 oracle
+"""The Newton's-third-law ("pair") kernel path, taken for N >= 32,768 (csrc/pair.cuh): ragged sizes around its tile
+sizes (I-tiles of 768, J-tiles of 128, 32-body systolic blocks), both integrators, against the FP64 oracle
 (<= 1e-5 per particle, north_star) and against the directed kernel of csrc/force.cuh on the same inputs."""
 
 import ctypes
@@ -18,7 +18,8 @@ KW = dict(total_mass=1.0, radial_scale=3.0, height_scale=0.3, g_const=4.5e-6, bl
 
 def _rows(n):
     """Sample of i-bodies: both ends, tile boundaries of the pair kernel, and a stride through the rest."""
-    edges = [0, 1, 31, 32, 383, 384, 1535, 1536, 1537, n - 1537, n - 385, n - 33, n - 32, n - 2, n - 1]
+    edges = [0, 1, 31, 32, 127, 128, 129, 383, 384, 767, 768, 769, 1535, 1536, 1537, n - 1537, n - 769, n - 385, n - 129,
+             n - 33, n - 32, n - 2, n - 1]
     return np.unique(np.clip(np.concatenate([edges, np.arange(7, n, n // 160)]), 0, n - 1))
 
 
@@ -46,7 +47,7 @@ def _directed_accelerations(pos, mass):
     return acc.cpu().numpy()
 
 
-@pytest.mark.parametrize("n", [65536, 65537, 66000, 70001, 98304 + 383, 131072, 200003])
+@pytest.mark.parametrize("n", [32768, 32769, 33000, 40001, 65536, 65537, 66000, 70001, 98304 + 383, 131072, 200003])
 def test_pair_path_accelerations_vs_oracle_and_directed_kernel(n):
     from galaxify import galaxies, simulation
 
@@ -110,10 +111,19 @@ def test_pair_path_trajectory_matches_directed_path(integrator, monkeypatch):
 
 
 def test_pair_path_is_what_runs_at_large_n():
-    """Launch accounting: one step at N = 65,536 is a pair launch + a finish launch (+ the O(N) prep)."""
+    """Launch accounting: one step at the pair path's lower limit is a pair launch + a finish launch (+ prep and plan),
+    and one body fewer takes the directed kernel (prep + one fused force launch)."""
     from galaxify import _native, galaxies, simulation
 
-    pos, vel, mass = galaxies.generate_disk(n_bodies=65536, seed=1, **KW)
+    n_min = _native.lib().nbody_pair_min_bodies()
+    assert n_min == 32768
+    pos, vel, mass = galaxies.generate_disk(n_bodies=n_min - 1, seed=1, **KW)
+    sim = simulation.LeapFrogSimulator(positions=pos, velocities=vel, masses=mass, calc_energy=False, **S01)
+    before = _native.launch_count()
+    sim.step()
+    torch.cuda.synchronize()
+    assert _native.launch_count() - before == 2  # prep, force
+    pos, vel, mass = galaxies.generate_disk(n_bodies=n_min, seed=1, **KW)
     sim = simulation.LeapFrogSimulator(positions=pos, velocities=vel, masses=mass, calc_energy=False, **S01)
     before = _native.launch_count()
     sim.step()
