@@ -72,3 +72,59 @@ def test_reference_arm_uses_every_host_thread_under_torchrun():
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip())
     assert d["cpu_baseline"]["cores"] == os.cpu_count()
+
+
+def _load_bench():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = argv
+    return mod
+
+
+def test_clock_warmup_and_sampler_logic():
+    """The timing hygiene helpers: extra warm-up steps from a post-warm-up probe, and a sampler that reports only the
+    samples taken inside the timed region (or the last one before it for very short regions)."""
+    import time
+
+    b = _load_bench()
+    assert b.clock_warmup_steps(0.003 * 3, 3) == int(b.CLOCK_WARMUP_SECONDS / 0.003)   # 3 ms steps: ~333 more
+    assert b.clock_warmup_steps(0.35 * 3, 3) == int(b.CLOCK_WARMUP_SECONDS / 0.35)      # 350 ms steps: 2 more
+    assert b.clock_warmup_steps(1e-9, 3) == 5000                                         # capped
+
+    class FakeNvml:
+        NVML_CLOCK_SM = 0
+
+        def nvmlDeviceGetClockInfo(self, h, k):
+            return 1965
+
+        def nvmlDeviceGetCurrentClocksEventReasons(self, h):
+            return 0x4 | 0x1  # sw_power_cap (kept and noted) + gpu_idle (ignored)
+
+    disabled = b.ClockSampler(0, enabled=False).start()
+    with disabled:
+        pass
+    assert disabled.summary()["sm_mhz"] is None  # ranks other than 0 do not poll
+
+    s = b.ClockSampler(0, period=0.01, enabled=False)
+    s.nv, s.h, s.max_mhz = FakeNvml(), None, 1965
+    s.start()
+    time.sleep(0.03)
+    with s:
+        time.sleep(0.06)
+    out = s.summary()
+    assert out["sm_mhz"] == 1965 and out["reasons"] == ["sw_power_cap"] and 2 <= out["samples"] <= 8 and "note" not in out
+
+    s = b.ClockSampler(0, period=0.5, enabled=False)
+    s.nv, s.h, s.max_mhz = FakeNvml(), None, 1965
+    s.start()
+    time.sleep(0.03)
+    with s:
+        time.sleep(0.01)
+    out = s.summary()
+    assert out["samples"] == 1 and "before it" in out["note"]

@@ -74,3 +74,52 @@ def test_shard_systems_is_a_balanced_partition(total, world):
         sizes.append(sl.stop - sl.start)
         nxt = sl.stop
     assert nxt == total and max(sizes) - min(sizes) <= 1
+
+
+@settings(max_examples=150, deadline=None)
+@given(n=st.integers(1, 1 << 21), world=st.integers(1, 16))
+def test_pair_blocks_partition_the_work(n, world):
+    """The pair path's blocks (nbody_shard_pair_blocks, a pure host function): over all ranks they contain exactly
+    n(n-1)/2 unordered pairs, stay inside the real bodies, and the sharded pair workspace is sized for them."""
+    if world > n:
+        return
+    lib = _native.lib()
+    n_pad, counts = shard_layout(n, world)
+    pairs = 0
+    buf = (ctypes.c_int * (5 * 16))()
+    for rank in range(world):
+        k = lib.nbody_shard_pair_blocks(n, world, n_pad, rank, buf, 16)
+        assert 1 <= k <= 16
+        lo = rank * n_pad
+        assert (buf[0], buf[1], buf[2], buf[3], buf[4]) == (lo, lo + counts[rank], lo, lo + counts[rank], 1)
+        pairs += counts[rank] * (counts[rank] - 1) // 2
+        for b in range(1, k):
+            i_lo, i_hi, j_lo, j_hi, tri = (buf[5 * b + c] for c in range(5))
+            assert tri == 0 and lo <= i_lo < i_hi <= lo + counts[rank]  # i-bodies are the rank's own
+            s = j_lo // n_pad
+            assert s != rank and s * n_pad <= j_lo < j_hi <= s * n_pad + counts[s]  # j-bodies of ONE other slot
+            pairs += (i_hi - i_lo) * (j_hi - j_lo)
+    assert pairs == n * (n - 1) // 2
+    assert lib.nbody_shard_pair_workspace_bytes(world, n_pad) > 0
+
+
+def test_rollout_and_integrator_entry_points_reject_bad_arguments_without_a_device():
+    """f4 (trainer.py:217-226): argument checks of the kick/drift entry points and of galaxify.rollout on the CPU."""
+    import pytest
+    import torch
+
+    from galaxify import rollout
+
+    lib = _native.lib()
+    buf = np.zeros(16, dtype=np.float32)
+    p = buf.ctypes.data
+    assert lib.nbody_kick_drift_f32(None, p, p, p, p, 4, 0.01, 0.005, None) == _native.ERR_INVALID_ARGUMENT
+    assert lib.nbody_kick_drift_f32(p, p, p, p, p, -1, 0.01, 0.005, None) == _native.ERR_INVALID_ARGUMENT
+    assert lib.nbody_kick_f32(p, None, p, 4, 0.005, None) == _native.ERR_INVALID_ARGUMENT
+    assert lib.nbody_momentum_f32(p, p, p, 0, p, None) == _native.ERR_INVALID_ARGUMENT
+    assert lib.nbody_pair_min_bodies() == 32768
+    z = torch.zeros((4, 3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rollout.kick_drift(z, z, z, 0.01)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rollout.step(lambda pos, feats: pos, z, z, torch.ones((4, 1)), z, 0.01)
